@@ -1,0 +1,20 @@
+// assembly.h -- host-side launcher interface of kernel 1 (assembly.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace emme {
+struct RunConst;
+
+// persistent grid size (SM count x resident CTAs) for the given Gauss-Kronrod order
+int assembly_grid_blocks(int order, int device);
+int assembly_groups_per_block(int order);
+int assembly_stack_smem();
+
+// Launch diagonal + quadrature kernels on `stream`.  `counter` (1 x u64), `stats` (8 x u64)
+// and `spill` (grid_blocks*groups_per_block*spill_cap double2, may be null when
+// spill_cap == 0) are device scratch owned by the handle.
+cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
+                            const double* bi, void* A, int shard_index, int shard_count,
+                            unsigned long long* counter, void* spill, int spill_cap,
+                            unsigned long long* stats, int grid_blocks, cudaStream_t stream);
+}  // namespace emme

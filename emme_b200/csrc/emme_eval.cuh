@@ -1,0 +1,251 @@
+// emme_eval.cuh -- per-node integrand evaluation of the EMME ion kernel (fp64).
+//
+// One call = one evaluation of the wrapped integrand g(x) = f(tan x)/cos^2 x that the
+// reference's util::integrate hands to Gauss-Kronrod (include/functions.h:315-318), with f
+// the lambda of Parameters::kappa_f_tau (src/Parameters.cpp:120-176) and the Miller
+// recurrence of util::bessel_i_alter_helper (include/functions.h:381-408) inlined.
+//
+// This is NOT a transcription: everything that depends only on the pair (eta, eta') is
+// hoisted into PairConst, divisions by complex numbers are replaced by one reciprocal of
+// lambda and one of mu, and two algebraic identities remove work per node:
+//     2 + i*beta_1/nu  ==  2*lambda            (nu = qR*deta/(vt*tau~))
+//     1/tau~           ==  conj(e)/t           (tau~ = t*e, |e| = 1)
+// so results agree with the reference to rounding (a few ulp per factor), not bit-for-bit.
+//
+// The functions are __host__ __device__ so that tests/emul (test infrastructure) can run the
+// same arithmetic on the CPU against the oracle before any GPU time is spent; the product
+// only ever calls them from kernels.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define EMME_HD __host__ __device__ __forceinline__
+#else
+#define EMME_HD inline
+#endif
+
+namespace emme {
+
+struct cplx {
+    double re, im;
+};
+
+EMME_HD cplx mk(double r, double i) { return cplx{r, i}; }
+EMME_HD cplx operator+(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
+EMME_HD cplx operator-(cplx a, cplx b) { return mk(a.re - b.re, a.im - b.im); }
+EMME_HD cplx operator-(cplx a) { return mk(-a.re, -a.im); }
+EMME_HD cplx operator*(cplx a, cplx b) {
+    return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+EMME_HD cplx operator*(double s, cplx a) { return mk(s * a.re, s * a.im); }
+EMME_HD cplx conj(cplx a) { return mk(a.re, -a.im); }
+EMME_HD double norm2(cplx a) { return a.re * a.re + a.im * a.im; }
+EMME_HD cplx recip(cplx a) {
+    const double d = 1.0 / norm2(a);
+    return mk(a.re * d, -a.im * d);
+}
+// i*a
+EMME_HD cplx mul_i(cplx a) { return mk(-a.im, a.re); }
+
+// Scalars of the run (one per assembly), precomputed on the host in the reference's own
+// association order so that they are bit-identical to what the reference multiplies by.
+struct RunConst {
+    double qR;          // q*R
+    double vt;
+    double arc;         // arc_coeff
+    double omega_s_i;
+    double eta_i;
+    double wsi_etai;    // omega_s_i*eta_i
+    double c_beta;      // (q*R)/vt*omega_d_bar          -> beta_1   = c_beta  *(g-g')
+    double c_beta_e;    // (q*R)/vt*(omega_d_bar*omega_s_e/omega_s_i)
+    double kappa_pref;  // (q*R)/(vt*sqrt(2*pi))         (src/Parameters.cpp:182-183)
+    double ke1_pref;    // (q*R)/(2*vt*tau)              (src/Parameters.cpp:196)
+    double ke2_pref;    // (q*q*R*R)/(2*vt*vt*tau)       (src/Parameters.cpp:200)
+    double vt_over_qR_num;  // unused placeholder keeps layout stable
+    double omega_s_e;
+    double eta_e;
+    double diag_es;     // 1 + 1/tau                     (include/solver.h:443)
+    double diag_em;     // (2*tau)/beta_e                (include/solver.h:469)
+    double tol, prec;   // integration_precision / integration_accuracy
+    double thr_len;     // 0.99*(b-a), b-a = pi/2        (include/functions.h:240)
+    double inv_scale;   // 2/(b-a)                       (include/functions.h:219)
+    double half_pi;     // b = pi/2
+    double dx;
+    double wr, wi;      // omega
+    double omi;         // -copysign(1, Re omega)        (src/Parameters.cpp:121)
+    int maxdepth;
+    int order;
+    int N;
+    int em;             // beta_e != 0
+};
+
+// Everything that depends on the pair (eta_i, eta_j) only.
+struct PairConst {
+    double deta;    // eta - eta'
+    double D;       // q*R*(eta-eta')
+    double Dv;      // D/vt
+    double beta1;   // beta_1(eta, eta')
+    double cl;      // 0.5*vt*beta1/D : lambda = 1 + i*cl*tau~
+    double s;       // sqrt(b*b')
+    double two_over_s;
+    double hb;      // 0.5*(b+b')
+    double bsum;    // b+b'
+    double c1;      // -omega_s_i*eta_i*s
+};
+
+EMME_HD PairConst make_pair(const RunConst& rc, double eta, double etap, double g, double gp,
+                            double b, double bp) {
+    PairConst pc;
+    pc.deta = eta - etap;
+    pc.D = rc.qR * pc.deta;
+    pc.Dv = pc.D / rc.vt;
+    pc.beta1 = rc.c_beta * (g - gp);
+    pc.cl = 0.5 * rc.vt * pc.beta1 / pc.D;
+    pc.s = sqrt(b * bp);
+    pc.two_over_s = 2.0 / pc.s;
+    pc.bsum = b + bp;
+    pc.hb = 0.5 * pc.bsum;
+    pc.c1 = -rc.omega_s_i * rc.eta_i * pc.s;
+    return pc;
+}
+
+struct EvalCounters {
+    unsigned int fwd, bwd;
+};
+
+// Scaled modified Bessel ratios by Miller's algorithm (include/functions.h:381-408).
+// z = s/lambda, zc = 2/z = (2/s)*lambda.  Returns y0, y1, mu(+y0); the 4th element of the
+// reference's array (-z or z) is formed by the caller.
+EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalCounters& cnt) {
+    const double THRESHOLD = 2.e+7;
+    const double az = sqrt(norm2(z));
+    int n = (int)(floor(az) + 1);
+    const int n0 = n;
+    // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared.
+    const double thr2 = fmax(THRESHOLD * ((double)n * sqrt(norm2(zc))), THRESHOLD * THRESHOLD);
+    cplx p0 = mk(0., 0.), p1 = mk(1., 0.);
+    while (norm2(p1) <= thr2) {
+        const cplx c = (double)n * zc;
+        const cplx pt = p0 - c * p1;
+        p0 = p1;
+        p1 = pt;
+        ++n;
+    }
+    cnt.fwd += (unsigned)(n - n0);
+    y0 = recip(p1);
+    y1 = mk(0., 0.);
+    mu = mk(0., 0.);
+    const bool neg = z.re < 0;
+    --n;
+    cnt.bwd += (unsigned)n;
+    for (; n > 0; --n) {
+        const cplx c = (double)n * zc;
+        const cplx yt = c * y0 + y1;
+        y1 = y0;
+        y0 = yt;
+        const double sg = neg ? (double)(2 - 4 * (n & 1)) : 2.0;
+        mu = mu + sg * y1;
+    }
+    mu = mu + y0;
+}
+
+// g(x) for mode m (0, 1, 2).  x in (0, pi/2).
+EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
+                       EvalCounters& cnt) {
+    const double c = cos(x);
+    const double t = tan(x);
+    // contour rotation e = exp(-i*omi*atan(t/arc)), tau~ = t*e   (src/Parameters.cpp:121-124)
+    const double u = t / rc.arc;
+    double sn, cs;
+    sincos(atan(u), &sn, &cs);
+    const cplx e = mk(cs, -rc.omi * sn);
+    const cplx taut = t * e;
+    // jacobian (:126-129): e - i*e*omi*t/(arc*(1+u^2))
+    const double jd = rc.omi * t / (rc.arc * (1.0 + u * u));
+    const cplx jacob = e - jd * mul_i(e);
+    // lambda = 1 + i*cl*tau~ (:101-106, :131)
+    const cplx lambda = mk(1.0 - pc.cl * taut.im, pc.cl * taut.re);
+    const cplx il = recip(lambda);
+    const cplx z = pc.s * il;                  // sqrt(b b')/lambda  (:135-136)
+    const cplx zc = pc.two_over_s * lambda;    // 2/z
+    const cplx z4 = z.re < 0 ? z : -z;         // include/functions.h:407
+    // nu = qR*deta/(vt*tau~) = (D/vt)/t * conj(e)   (:140)
+    const double it = 1.0 / t;
+    const cplx itaut = it * conj(e);           // 1/tau~
+    const cplx nu = pc.Dv * itaut;
+    const cplx nu2 = nu * nu;
+    // log of the exponential factor (:157-164); 2 + i*beta1/nu == 2*lambda
+    const cplx L = (-0.5) * nu2 + (0.5 * pc.beta1) * mk(nu.im, -nu.re) +
+                   mul_i(taut * mk(rc.wr, rc.wi)) - pc.hb * il;
+    const cplx arg = L - z4;
+    if (arg.re < -40.) return mk(0., 0.);      // safe_exp underflow guard (:167-173)
+
+    cplx y0, y1, mu;
+    bessel_i_alter(z, zc, y0, y1, mu, cnt);
+
+    const cplx il3 = il * il * il;             // pow(lambda, -3.)   (:138-139)
+    // i0_coef, i1_coef (:142-151)
+    const cplx inner = mk(1.0 + rc.eta_i * (0.5 * nu2.re - 1.5), rc.eta_i * (0.5 * nu2.im));
+    const cplx i0 = (mk(rc.wr, rc.wi) - rc.omega_s_i * inner) * il +
+                    rc.wsi_etai * (mk(pc.hb, 0.) - lambda) * il3;
+    const cplx i1 = pc.c1 * il3;
+
+    double es, ec;
+    sincos(arg.im, &es, &ec);
+    const double er = exp(arg.re);
+    const cplx se = mk(er * ec, er * es);
+
+    cplx pw = itaut;                           // nu^m / tau~        (:174)
+    if (m >= 1) pw = pw * nu;
+    if (m >= 2) pw = pw * nu;
+    const cplx f = pw * jacob * se * (i0 * y0 + i1 * y1) * recip(mu);
+    const double ic2 = 1.0 / (c * c);          // include/functions.h:317
+    return ic2 * f;
+}
+
+// Closed-form electron part (src/Parameters.cpp:186-209), m = 1, 2 (m = 0 is zero).
+EMME_HD cplx kappa_e(const RunConst& rc, int m, double deta, double dg) {
+    const cplx w = mk(rc.wr, rc.wi);
+    const double sgn_num = deta, sgn_den = fabs(deta);
+    if (m == 1) {
+        const cplx a = mk(rc.wr - rc.omega_s_e, rc.wi);
+        cplx k = mk(rc.ke1_pref * a.im, -rc.ke1_pref * a.re);  // -i*pref*(omega-omega_s_e)
+        k = sgn_num * k;
+        return mk(k.re / sgn_den, k.im / sgn_den);
+    }
+    if (m == 2) {
+        const double pref = rc.ke2_pref * sgn_num / sgn_den;
+        const cplx t1 = deta * (w * mk(rc.wr - rc.omega_s_e, rc.wi));
+        const double b1e = rc.c_beta_e * dg;
+        const double c2 = b1e * rc.vt / rc.qR;
+        const cplx t2 = c2 * mk(rc.wr - rc.omega_s_e * (1.0 + rc.eta_e), rc.wi);
+        return pref * (t1 - t2);
+    }
+    return mk(0., 0.);
+}
+
+// SingularityHandler(n)(i,j) on the fly (src/singularity_handler.cpp:3-24).
+EMME_HD double sing_weight(int n, int i, int j) {
+    const int diff = i > j ? i - j : j - i;
+    double w;
+    switch (diff) {
+        case 0: w = 0.0; break;
+        case 1: w = 2.951388888888883; break;
+        case 2: w = -2.4305555555555305; break;
+        case 3: w = 4.166666666667441; break;
+        case 4: w = -0.3472222222224549; break;
+        case 5: w = 1.159722222222284; break;
+        default: w = 1.0; break;
+    }
+    if (j == 0 || j == n - 1) w -= 0.5;
+    return w;
+}
+
+// ---- Gauss-Kronrod tables (include/functions.h:92-162).  Index 0 is the centre node. ----
+struct GKTables {
+    double a[16];   // abscissae
+    double kw[16];  // Kronrod weights
+    double gw[16];  // Gauss weight of node i (0 for pure Kronrod nodes)
+};
+
+}  // namespace emme

@@ -1,0 +1,145 @@
+/* emme_b200.h -- C ABI of the B200-native EMME eigen hot path.
+ *
+ * Drop-in boundary for the one data-parallel path of ssskkkky/EMME: the assembly of
+ * the eigenmatrix A(omega) and the dense step of the Newton/secant root find.  The
+ * reference has no FFI of its own; the entry points below are what a maintainer
+ * would bind in place of the C++ members listed next to each of them (file:line in
+ * the reference tree).  Plain pointers and sizes only -- no C++, CUDA or torch types.
+ *
+ * Conventions
+ *   - every function returns an int status in the style of LAPACK's `info`
+ *     (include/solver.h:121,142-153 of the reference): 0 = ok, <0 = argument -k had an
+ *     illegal value, >0 = numerical or device failure (see EMME_E_*).
+ *     emme_last_error() gives the text for the calling thread's last failure.
+ *   - matrices are complex128, row-major, dim x dim, dim = npoints (beta_e == 0) or
+ *     2*npoints -- the layout of Matrix<std::complex<double>> (include/Matrix.h:43) and of
+ *     eigenMatrics/*.bin (src/main.cpp:61-63).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with EMME_E_NO_DEVICE.
+ *   - a handle is not re-entrant (like the reference's EigenSolver); different handles may
+ *     be used from different threads / processes / devices.
+ */
+#ifndef EMME_B200_H
+#define EMME_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMME_E_NO_DEVICE 1000   /* no usable CUDA device / CUDA runtime error       */
+#define EMME_E_SINGULAR_BASE 0  /* 1..dim: pivot k exactly zero (LAPACK info > 0)   */
+#define EMME_E_CUDA 1001        /* a CUDA call failed; text in emme_last_error()    */
+#define EMME_E_BAD_ORDER 1002   /* integration_start_points not 15 or 31            */
+#define EMME_E_STATE 1003       /* call sequence error (e.g. step before seed)      */
+#define EMME_E_INPUT 1004       /* input.json error; text in emme_last_error()      */
+
+/* The scalars the hot path reads from the reference's Parameters object
+ * (include/Parameters.h:15-43) plus the mesh spacing of Grid<double> (include/Grid.h:11). */
+typedef struct emme_params {
+    double q, R, vt, tau, beta_e;
+    double eta_i, eta_e;
+    double omega_s_i, omega_s_e, omega_d_bar; /* derived, src/Parameters.cpp:62-64 */
+    double arc_coeff;
+    double integration_precision; /* tol,   src/Parameters.cpp:178 */
+    double integration_accuracy;  /* prec,  src/Parameters.cpp:179 */
+    int integration_iteration_limit; /* max bisection depth */
+    int integration_start_points;    /* 15 or 31            */
+    double dx;                       /* Grid::dx            */
+} emme_params;
+
+/* Work and time counters of the most recent assembly on a handle. */
+typedef struct emme_stats {
+    unsigned long long integrals; /* adaptive quadratures                         */
+    unsigned long long panels;    /* Gauss-Kronrod panels                          */
+    unsigned long long evals;     /* integrand evaluations                         */
+    unsigned long long fwd_trips; /* Miller forward-recurrence trips               */
+    unsigned long long bwd_trips; /* Miller backward-recurrence trips              */
+    unsigned long long max_stack; /* deepest interval stack seen                   */
+    double assemble_ms;           /* CUDA-event time of the last assembly kernel    */
+    double dense_ms;              /* CUDA-event time of the last dense step         */
+} emme_stats;
+
+typedef struct emme_solver emme_solver; /* opaque; owns device memory */
+
+/* ---- device / library ---- */
+int emme_device_count(void);
+const char* emme_last_error(void);
+const char* emme_version(void);
+
+/* ---- solver life cycle --------------------------------------------------------------
+ * Replaces the construction of Parameters / Grid / SingularityHandler / EigenSolver in
+ * solve_once_eigen (src/main.cpp:27-37).  eta, g, bi are npoints doubles each:
+ * eta[i] = Grid::grid[i] (include/Grid.h:13), g[i] = para.g_integration_f(eta[i]) and
+ * bi[i] = para.bi(eta[i]) (src/Parameters.cpp:76-100 and the geometry overrides); the
+ * singular-diagonal weights of SingularityHandler (src/singularity_handler.cpp:3-24) are
+ * computed on the fly.  The arrays are copied; the caller keeps ownership. */
+int emme_create(const emme_params* p, int npoints, const double* eta, const double* g,
+                const double* bi, int device, emme_solver** out);
+int emme_destroy(emme_solver* s);
+int emme_dim(const emme_solver* s);
+
+/* ---- A(omega): EigenSolver::matrixAssembler (include/solver.h:417-515) ---------------
+ * emme_assemble        : into caller's HOST buffer (dim*dim complex128, row-major).
+ * emme_assemble_device : into caller's DEVICE buffer on the handle's device; only the
+ *   work items k with k % shard_count == shard_index are computed (pairs i<j in
+ *   diagonal-major order); with shard_count == 1 the full matrix incl. the
+ *   diagonal is written.  Used for multi-GPU assembly: every rank fills its share of a
+ *   zero-initialised buffer and the shares are summed/gathered by the caller. */
+int emme_assemble(emme_solver* s, double wr, double wi, void* host_out);
+int emme_assemble_device(emme_solver* s, double wr, double wi, void* dev_out, int shard_index,
+                         int shard_count);
+
+/* ---- Newton / secant root find (include/solver.h:396-415 and :113-160) ---------------
+ * emme_seed: the EigenSolver constructor: omega = 0.99*w0, delta = 0.01*w0, A_old =
+ *   A(omega), omega += delta, A = A(omega), A' = (A - A_old)/delta.
+ * emme_newton_trace_step: newtonTraceSecantIteration: solve A X = A', delta = -1/tr X,
+ *   omega += delta, re-assemble, A' = (A - A_old)/delta.  Outputs the new eigen_value and
+ *   d_eigen_value.  Returns k > 0 if pivot k is exactly zero (the reference's
+ *   "Linear solve failed" runtime_error, include/solver.h:142-153).
+ * emme_trace_delta: only the dense part on caller-provided HOST matrices (for tests):
+ *   delta = -1/trace(A^-1 Ad). */
+int emme_seed(emme_solver* s, double w0r, double w0i);
+int emme_newton_trace_step(emme_solver* s, double* wr, double* wi, double* dr, double* di);
+int emme_get_eigen_value(const emme_solver* s, double* wr, double* wi, double* dr, double* di);
+int emme_trace_delta(emme_solver* s, const void* host_A, const void* host_Ad, double* dr,
+                     double* di);
+
+/* Multi-GPU variant of the two calls above: the assemblies inside seed/step are split
+ * into (begin: launch my shard into the handle's A buffer) and (finish: after the caller
+ * has completed the matrix in that buffer, e.g. by an NCCL all-reduce/all-gather on the
+ * device pointer returned by emme_matrix_device_ptr).  See emme_b200/parallel.py. */
+int emme_shard_config(emme_solver* s, int shard_index, int shard_count);
+int emme_seed_begin(emme_solver* s, double w0r, double w0i);   /* assemble shard at 0.99 w0 */
+int emme_seed_middle(emme_solver* s);                          /* A_old<-A, omega+=delta, assemble shard */
+int emme_seed_finish(emme_solver* s);                          /* A' = (A-A_old)/delta */
+int emme_step_begin(emme_solver* s);                           /* dense step, omega+=delta, assemble shard */
+int emme_step_finish(emme_solver* s, double* wr, double* wi, double* dr, double* di);
+void* emme_matrix_device_ptr(emme_solver* s, int which);
+
+/* which: 0 = eigen_matrix, 1 = eigen_matrix_old, 2 = eigen_matrix_derivative
+ * (the three public matrices of EigenSolver, include/solver.h:392-394). */
+int emme_copy_matrix(emme_solver* s, int which, void* host_out);
+int emme_get_stats(const emme_solver* s, emme_stats* out);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for event timing. */
+void* emme_stream(emme_solver* s);
+int emme_synchronize(emme_solver* s);
+
+/* ---- host side: input.json -> emme_params + tables -----------------------------------
+ * Replaces util::json::parse_file + Parameters::generate + Grid (src/main.cpp:184,27-32;
+ * src/Parameters.cpp:10-66; include/Grid.h:8-14) for callers that do not have the
+ * reference's objects.  Scan objects {head, step, tail} collapse to their head
+ * (filter_input, src/main.cpp:174-180). */
+typedef struct emme_input emme_input;
+int emme_input_load(const char* path, emme_input** out);
+int emme_input_parse(const char* json_text, emme_input** out);
+void emme_input_free(emme_input* in);
+int emme_input_set_number(emme_input* in, const char* key, double value);
+int emme_input_get_number(const emme_input* in, const char* key, double* value);
+int emme_input_get_string(const emme_input* in, const char* key, char* buf, int buflen);
+int emme_input_params(const emme_input* in, emme_params* p, int* npoints);
+int emme_input_tables(const emme_input* in, double* eta, double* g, double* bi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMME_B200_H */
