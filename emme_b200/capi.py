@@ -1,0 +1,105 @@
+"""ctypes binding of the C ABI in include/emme_b200.h (libemme_b200.so).
+
+The library is the product; this module only declares prototypes.  Loading fails loudly if
+the shared object is missing -- there is no Python or CPU fallback for the compute path.
+"""
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libemme_b200.so"
+
+E_NO_DEVICE, E_CUDA, E_BAD_ORDER, E_STATE, E_INPUT = 1000, 1001, 1002, 1003, 1004
+
+
+class EmmeParams(C.Structure):
+    """struct emme_params"""
+    _fields_ = [(n, C.c_double) for n in
+                ("q", "R", "vt", "tau", "beta_e", "eta_i", "eta_e", "omega_s_i", "omega_s_e",
+                 "omega_d_bar", "arc_coeff", "integration_precision", "integration_accuracy")] + [
+        ("integration_iteration_limit", C.c_int), ("integration_start_points", C.c_int),
+        ("dx", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class EmmeStats(C.Structure):
+    """struct emme_stats"""
+    _fields_ = [(n, C.c_ulonglong) for n in
+                ("integrals", "panels", "evals", "fwd_trips", "bwd_trips", "max_stack")] + [
+        ("assemble_ms", C.c_double), ("dense_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/emme_b200.h declares: name -> (restype, argtypes)
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+PROTOTYPES = {
+    "emme_device_count": (C.c_int, []),
+    "emme_last_error": (C.c_char_p, []),
+    "emme_version": (C.c_char_p, []),
+    "emme_create": (C.c_int, [C.POINTER(EmmeParams), C.c_int, _dp, _dp, _dp, C.c_int, C.POINTER(_vp)]),
+    "emme_destroy": (C.c_int, [_vp]),
+    "emme_dim": (C.c_int, [_vp]),
+    "emme_assemble": (C.c_int, [_vp, C.c_double, C.c_double, _vp]),
+    "emme_assemble_device": (C.c_int, [_vp, C.c_double, C.c_double, _vp, C.c_int, C.c_int]),
+    "emme_seed": (C.c_int, [_vp, C.c_double, C.c_double]),
+    "emme_newton_trace_step": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "emme_get_eigen_value": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "emme_trace_delta": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
+    "emme_shard_config": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "emme_seed_begin": (C.c_int, [_vp, C.c_double, C.c_double]),
+    "emme_seed_middle": (C.c_int, [_vp]),
+    "emme_seed_finish": (C.c_int, [_vp]),
+    "emme_step_begin": (C.c_int, [_vp]),
+    "emme_step_finish": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "emme_matrix_device_ptr": (_vp, [_vp, C.c_int]),
+    "emme_copy_matrix": (C.c_int, [_vp, C.c_int, _vp]),
+    "emme_get_stats": (C.c_int, [_vp, C.POINTER(EmmeStats)]),
+    "emme_stream": (_vp, [_vp]),
+    "emme_synchronize": (C.c_int, [_vp]),
+    "emme_input_load": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "emme_input_parse": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "emme_input_free": (None, [_vp]),
+    "emme_input_set_number": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "emme_input_get_number": (C.c_int, [_vp, C.c_char_p, _dp]),
+    "emme_input_get_string": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_int]),
+    "emme_input_params": (C.c_int, [_vp, C.POINTER(EmmeParams), C.POINTER(C.c_int)]),
+    "emme_input_tables": (C.c_int, [_vp, _dp, _dp, _dp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libemme_b200.so (building nothing: see emme_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m emme_b200.build` "
+                "(emme_b200 has no CPU fallback)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError = a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class EmmeError(RuntimeError):
+    """Raised for a non-zero status of the C ABI; .code is the LAPACK-style info."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+def check(code):
+    if code != 0:
+        msg = load().emme_last_error()
+        raise EmmeError(code, (msg or b"").decode() or f"emme_b200 status {code}")

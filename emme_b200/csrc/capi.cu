@@ -1,0 +1,501 @@
+// capi.cu -- the C ABI of include/emme_b200.h: handle management, the Newton/secant state
+// machine of EigenSolver (reference include/solver.h:396-415, 113-160) around kernels 1 and 2,
+// and the host-side input helpers.  No CPU fallback: every compute entry point needs a device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/emme_b200.h"
+#include "../host/json.hpp"
+#include "../host/parameters.hpp"
+#include "assembly.h"
+#include "dense.h"
+#include "run_const.h"
+
+using emme::RunConst;
+typedef std::complex<double> zc;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(EMME_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+struct emme_solver {
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    emme_params p{};
+    int N = 0, dim = 0;
+    double *d_eta = nullptr, *d_g = nullptr, *d_bi = nullptr;
+    // the three public matrices of EigenSolver + LU work copy
+    void *A = nullptr, *Aold = nullptr, *Ad = nullptr, *W = nullptr;
+    unsigned long long *d_counter = nullptr, *d_stats = nullptr;
+    void* d_spill = nullptr;
+    int spill_cap = 0, grid_blocks = 0;
+    void* d_dense_ws = nullptr;
+    double2* d_trace = nullptr;
+    int* d_info = nullptr;
+    // Newton state
+    bool seeded = false;
+    zc w{0, 0}, dw{0, 0};
+    int shard_index = 0, shard_count = 1;
+    emme_stats stats{};
+    size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
+};
+
+extern "C" {
+
+const char* emme_last_error(void) { return g_err.c_str(); }
+const char* emme_version(void) { return "emme_b200 0.1 (sm_100a)"; }
+
+int emme_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int emme_dim(const emme_solver* s) { return s ? s->dim : -1; }
+
+int emme_destroy(emme_solver* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_eta);
+    cudaFree(s->d_g);
+    cudaFree(s->d_bi);
+    cudaFree(s->A);
+    cudaFree(s->Aold);
+    cudaFree(s->Ad);
+    cudaFree(s->W);
+    cudaFree(s->d_counter);
+    cudaFree(s->d_stats);
+    cudaFree(s->d_spill);
+    cudaFree(s->d_dense_ws);
+    cudaFree(s->d_trace);
+    cudaFree(s->d_info);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+int emme_create(const emme_params* p, int npoints, const double* eta, const double* g,
+                const double* bi, int device, emme_solver** out) {
+    if (!p) return fail(-1, "emme_create: params is null");
+    if (npoints < 2) return fail(-2, "emme_create: npoints < 2");
+    if (!eta) return fail(-3, "emme_create: eta is null");
+    if (!g) return fail(-4, "emme_create: g is null");
+    if (!bi) return fail(-5, "emme_create: bi is null");
+    if (!out) return fail(-7, "emme_create: out is null");
+    if (p->integration_start_points != 15 && p->integration_start_points != 31)
+        return fail(EMME_E_BAD_ORDER, "integration_start_points should be 15 or 31");
+    int ndev = emme_device_count();
+    if (ndev <= 0) return fail(EMME_E_NO_DEVICE, "no CUDA device: emme_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(-6, "emme_create: device out of range");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<emme_solver, int (*)(emme_solver*)> s(new emme_solver, emme_destroy);
+    s->device = device;
+    s->p = *p;
+    s->N = npoints;
+    s->dim = std::fpclassify(p->beta_e) == FP_ZERO ? npoints : 2 * npoints;
+    CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    const size_t tb = sizeof(double) * npoints;
+    CU(cudaMalloc(&s->d_eta, tb));
+    CU(cudaMalloc(&s->d_g, tb));
+    CU(cudaMalloc(&s->d_bi, tb));
+    CU(cudaMemcpy(s->d_eta, eta, tb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_g, g, tb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_bi, bi, tb, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&s->A, s->bytes()));
+    CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    CU(cudaMalloc(&s->d_stats, 8 * sizeof(unsigned long long)));
+    s->grid_blocks = emme::assembly_grid_blocks(p->integration_start_points, device);
+    // interval stack: at most integration_iteration_limit + 1 live entries
+    s->spill_cap = p->integration_iteration_limit + 2 - emme::assembly_stack_smem();
+    if (s->spill_cap < 0) s->spill_cap = 0;
+    if (s->spill_cap > 0) {
+        const size_t groups = (size_t)s->grid_blocks *
+                              emme::assembly_groups_per_block(p->integration_start_points);
+        CU(cudaMalloc(&s->d_spill, groups * s->spill_cap * sizeof(double2)));
+    }
+    CU(cudaMalloc(&s->d_trace, sizeof(double2)));
+    CU(cudaMalloc(&s->d_info, sizeof(int)));
+    *out = s.release();
+    return 0;
+}
+
+static int ensure_newton_buffers(emme_solver* s) {
+    if (!s->Aold) CU(cudaMalloc(&s->Aold, s->bytes()));
+    if (!s->Ad) CU(cudaMalloc(&s->Ad, s->bytes()));
+    if (!s->W) CU(cudaMalloc(&s->W, s->bytes()));
+    if (!s->d_dense_ws) CU(cudaMalloc(&s->d_dense_ws, emme::dense_workspace_bytes(s->dim)));
+    return 0;
+}
+
+// enqueue one assembly of A(w) into `dst` (device), this handle's shard only
+static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, int shard_count) {
+    RunConst rc = emme::make_run_const(s->p, s->N, w.real(), w.imag());
+    CU(cudaEventRecord(s->ev0, s->stream));
+    CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, dst, shard_index, shard_count,
+                             s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->grid_blocks,
+                             s->stream));
+    CU(cudaEventRecord(s->ev1, s->stream));
+    return 0;
+}
+
+static int collect_stats(emme_solver* s) {
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->stats.integrals = h[0];
+    s->stats.panels = h[1];
+    s->stats.evals = h[2];
+    s->stats.fwd_trips = h[3];
+    s->stats.bwd_trips = h[4];
+    s->stats.max_stack = h[5];
+    s->stats.assemble_ms = ms;
+    return 0;
+}
+
+int emme_assemble_device(emme_solver* s, double wr, double wi, void* dev_out, int shard_index,
+                         int shard_count) {
+    if (!s) return fail(-1, "emme_assemble_device: null handle");
+    if (!dev_out) return fail(-4, "emme_assemble_device: null output");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+        return fail(-5, "emme_assemble_device: bad shard");
+    CU(cudaSetDevice(s->device));
+    int rc = enqueue_assembly(s, zc(wr, wi), dev_out, shard_index, shard_count);
+    if (rc) return rc;
+    return collect_stats(s);
+}
+
+int emme_assemble(emme_solver* s, double wr, double wi, void* host_out) {
+    if (!s) return fail(-1, "emme_assemble: null handle");
+    if (!host_out) return fail(-4, "emme_assemble: null output");
+    CU(cudaSetDevice(s->device));
+    int rc = enqueue_assembly(s, zc(wr, wi), s->A, 0, 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host_out, s->A, s->bytes(), cudaMemcpyDeviceToHost, s->stream));
+    return collect_stats(s);
+}
+
+// ---- dense step on (A, Ad): delta = -1/trace(A^-1 Ad); A is preserved, Ad destroyed ----
+static int dense_delta(emme_solver* s, zc* delta) {
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, s->stream));
+    CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
+    CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
+                                s->stream));
+    CU(cudaEventRecord(e1, s->stream));
+    double tr[2];
+    int info = 0;
+    CU(cudaMemcpyAsync(tr, s->d_trace, sizeof tr, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    s->stats.dense_ms = ms;
+    // d_eigen_value = -1.0 / trace   (include/solver.h:139)
+    *delta = -1.0 / zc(tr[0], tr[1]);
+    if (info != 0) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf,
+                      "Linear solve failed. The factorization has been completed, but the pivot "
+                      "is exactly singular at %d, so the solution could not be computed.", info);
+        return fail(info, buf);
+    }
+    return 0;
+}
+
+static int secant(emme_solver* s) {
+    CU(emme::launch_secant(s->A, s->Aold, s->Ad, (size_t)s->dim * s->dim, s->dw.real(),
+                           s->dw.imag(), s->sms, s->stream));
+    return 0;
+}
+
+int emme_shard_config(emme_solver* s, int shard_index, int shard_count) {
+    if (!s) return fail(-1, "null handle");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+        return fail(-2, "emme_shard_config: bad shard");
+    s->shard_index = shard_index;
+    s->shard_count = shard_count;
+    return 0;
+}
+
+// When sharded, the caller completes the matrix between begin/middle/finish; the buffer is
+// zeroed first so that shares can be summed.
+static int assemble_current(emme_solver* s) {
+    if (s->shard_count > 1) CU(cudaMemsetAsync(s->A, 0, s->bytes(), s->stream));
+    int rc = enqueue_assembly(s, s->w, s->A, s->shard_index, s->shard_count);
+    if (rc) return rc;
+    return collect_stats(s);
+}
+
+int emme_seed_begin(emme_solver* s, double w0r, double w0i) {
+    if (!s) return fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_newton_buffers(s);
+    if (rc) return rc;
+    const zc w0(w0r, w0i);
+    s->w = 0.99 * w0;   // include/solver.h:401
+    s->dw = 0.01 * w0;  // include/solver.h:402
+    s->seeded = false;
+    return assemble_current(s);  // eigen_matrix_old = A(0.99 w0), :411 (swapped in seed_middle)
+}
+
+int emme_seed_middle(emme_solver* s) {
+    if (!s) return fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    std::swap(s->A, s->Aold);
+    s->w += s->dw;  // :412
+    return assemble_current(s);  // :413
+}
+
+int emme_seed_finish(emme_solver* s) {
+    if (!s) return fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    int rc = secant(s);  // :414
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->seeded = true;
+    return 0;
+}
+
+int emme_seed(emme_solver* s, double w0r, double w0i) {
+    int rc = emme_seed_begin(s, w0r, w0i);
+    if (rc) return rc;
+    rc = emme_seed_middle(s);
+    if (rc) return rc;
+    return emme_seed_finish(s);
+}
+
+int emme_step_begin(emme_solver* s) {
+    if (!s) return fail(-1, "null handle");
+    if (!s->seeded) return fail(EMME_E_STATE, "emme_newton_trace_step before emme_seed");
+    CU(cudaSetDevice(s->device));
+    zc delta;
+    int rc = dense_delta(s, &delta);  // include/solver.h:130-139
+    s->dw = delta;
+    s->w += delta;  // :140 (the reference updates omega before it checks info)
+    if (rc) return rc;
+    std::swap(s->A, s->Aold);  // eigen_matrix_old = eigen_matrix (:114) without a copy
+    return assemble_current(s);  // :157
+}
+
+int emme_step_finish(emme_solver* s, double* wr, double* wi, double* dr, double* di) {
+    if (!s) return fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    int rc = secant(s);  // :159
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    if (wr) *wr = s->w.real();
+    if (wi) *wi = s->w.imag();
+    if (dr) *dr = s->dw.real();
+    if (di) *di = s->dw.imag();
+    return 0;
+}
+
+int emme_newton_trace_step(emme_solver* s, double* wr, double* wi, double* dr, double* di) {
+    int rc = emme_step_begin(s);
+    if (rc) return rc;
+    return emme_step_finish(s, wr, wi, dr, di);
+}
+
+int emme_get_eigen_value(const emme_solver* s, double* wr, double* wi, double* dr, double* di) {
+    if (!s) return fail(-1, "null handle");
+    if (wr) *wr = s->w.real();
+    if (wi) *wi = s->w.imag();
+    if (dr) *dr = s->dw.real();
+    if (di) *di = s->dw.imag();
+    return 0;
+}
+
+int emme_trace_delta(emme_solver* s, const void* host_A, const void* host_Ad, double* dr,
+                     double* di) {
+    if (!s) return fail(-1, "null handle");
+    if (!host_A) return fail(-2, "null A");
+    if (!host_Ad) return fail(-3, "null Ad");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_newton_buffers(s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->A, host_A, s->bytes(), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->Ad, host_Ad, s->bytes(), cudaMemcpyHostToDevice, s->stream));
+    zc delta;
+    rc = dense_delta(s, &delta);
+    if (dr) *dr = delta.real();
+    if (di) *di = delta.imag();
+    return rc;
+}
+
+void* emme_matrix_device_ptr(emme_solver* s, int which) {
+    if (!s) return nullptr;
+    return which == 0 ? s->A : which == 1 ? s->Aold : which == 2 ? s->Ad : nullptr;
+}
+
+int emme_copy_matrix(emme_solver* s, int which, void* host_out) {
+    if (!s) return fail(-1, "null handle");
+    if (which < 0 || which > 2) return fail(-2, "emme_copy_matrix: which must be 0, 1 or 2");
+    if (!host_out) return fail(-3, "null output");
+    void* src = emme_matrix_device_ptr(s, which);
+    if (!src) return fail(EMME_E_STATE, "matrix not allocated yet (call emme_seed first)");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(host_out, src, s->bytes(), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int emme_get_stats(const emme_solver* s, emme_stats* out) {
+    if (!s) return fail(-1, "null handle");
+    if (!out) return fail(-2, "null output");
+    *out = s->stats;
+    return 0;
+}
+
+void* emme_stream(emme_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int emme_synchronize(emme_solver* s) {
+    if (!s) return fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ host-side input helpers
+struct emme_input {
+    emme::json::Value json;  // scan objects already collapsed to their head
+};
+
+static int finish_input(emme::json::Value all, emme_input** out) {
+    // filter_input (src/main.cpp:174-180)
+    emme::json::Value in = all.clone();
+    for (auto& [key, val] : in.as_object()) {
+        if (val.is_object() && val.contains("head")) {
+            emme::json::Value head = val.at("head");
+            val = head;
+        }
+    }
+    *out = new emme_input{std::move(in)};
+    return 0;
+}
+
+int emme_input_load(const char* path, emme_input** out) {
+    if (!path) return fail(-1, "null path");
+    if (!out) return fail(-2, "null out");
+    try {
+        return finish_input(emme::json::parse_file(path), out);
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+int emme_input_parse(const char* text, emme_input** out) {
+    if (!text) return fail(-1, "null text");
+    if (!out) return fail(-2, "null out");
+    try {
+        return finish_input(emme::json::parse(std::string(text)), out);
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+void emme_input_free(emme_input* in) { delete in; }
+
+int emme_input_set_number(emme_input* in, const char* key, double value) {
+    if (!in) return fail(-1, "null input");
+    if (!key) return fail(-2, "null key");
+    in->json[std::string(key)] = emme::json::Value(value);
+    return 0;
+}
+
+int emme_input_get_number(const emme_input* in, const char* key, double* value) {
+    if (!in) return fail(-1, "null input");
+    if (!key) return fail(-2, "null key");
+    try {
+        // "name[k]" addresses element k of an array value, e.g. initial_guess[0]
+        std::string k(key);
+        double v;
+        const size_t lb = k.find('[');
+        if (lb != std::string::npos && k.back() == ']') {
+            const size_t idx = (size_t)std::atoi(k.substr(lb + 1, k.size() - lb - 2).c_str());
+            v = in->json.at(k.substr(0, lb)).at(idx).number();
+        } else {
+            v = in->json.at(k).number();
+        }
+        if (value) *value = v;
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+int emme_input_get_string(const emme_input* in, const char* key, char* buf, int buflen) {
+    if (!in) return fail(-1, "null input");
+    if (!key) return fail(-2, "null key");
+    try {
+        const std::string& v = in->json.at(key).as_string();
+        if (buf && buflen > 0) {
+            std::strncpy(buf, v.c_str(), buflen - 1);
+            buf[buflen - 1] = 0;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+int emme_input_params(const emme_input* in, emme_params* p, int* npoints) {
+    if (!in) return fail(-1, "null input");
+    try {
+        auto para = emme::Parameters::generate(in->json);
+        if (p) *p = para->to_pod();
+        if (npoints) *npoints = para->npoints;
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+int emme_input_tables(const emme_input* in, double* eta, double* g, double* bi) {
+    if (!in) return fail(-1, "null input");
+    try {
+        auto para = emme::Parameters::generate(in->json);
+        std::vector<double> e, gg, b;
+        para->tables(e, gg, b);
+        const size_t nb = sizeof(double) * e.size();
+        if (eta) std::memcpy(eta, e.data(), nb);
+        if (g) std::memcpy(g, gg.data(), nb);
+        if (bi) std::memcpy(bi, b.data(), nb);
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+// dense.h -- host-side launcher interface of kernel 2 (dense.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#define DENSE_NB 32
+
+namespace emme {
+// device scratch needed by launch_trace_solve for a dim x dim system
+size_t dense_workspace_bytes(int dim);
+// trace(W^-1 B) -> *d_trace (double2 on device); W and B (dim x dim complex128, row-major)
+// are destroyed.  *d_info (device int): 0 or k > 0 if pivot k is exactly zero.
+cudaError_t launch_trace_solve(void* W, void* B, int dim, void* workspace, void* d_trace,
+                               int* d_info, cudaStream_t stream);
+// Ad = (A - Aold)/delta over n complex entries
+cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,
+                          double di, int sms, cudaStream_t stream);
+}  // namespace emme

@@ -1,0 +1,131 @@
+"""-m gpu: kernel 1 (CUDA assembly through the C ABI) against the reference goldens and the oracle."""
+import numpy as np
+import pytest
+
+import cases
+import parity
+from emme_b200 import EigenSolver, Input
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["c1_n32", "c1_n64", "c1_n128", "c1_gk31_n128", "c1_em_n64", "c1_pos_n64", "c1_cyl_n64",
+         "c1_tmd_n64", "c1_cylold_n64", "c3_n32", "c3_n64", "c3_n128"]
+
+
+def report(label, c, st=None):
+    print(f"\n[parity] {label}: entries={c['entries']} strict_frac={c['strict_frac']:.6f} "
+          f"max_rel={c['max_rel']:.3e} median_rel={c['median_rel']:.3e} max_abs={c['max_abs']:.3e} "
+          f"max_abs/max|A|={c['max_abs_over_max']:.3e} n_rel>1e-9={c['n_rel_gt_1e9']}"
+          + (f" stats={st}" if st else ""))
+
+
+@pytest.mark.parametrize("case", SMALL)
+def test_assembly_matches_reference_golden(case, golden, floor, native_lib):
+    inp = Input(cases.input_path(case))
+    s = EigenSolver.from_input(inp)
+    w = complex(*golden["assemble"][case]["omega"])
+    A = s.matrixAssembler(w)
+    ref = cases.ref_matrix(case)
+    em = s.dim != s.npoints
+    c = parity.assert_parity(A, ref, em=em, label=case)
+    report(case, c, s.stats())
+    # not worse than a small multiple of the reference's own FMA/no-FMA self-deviation
+    assert c["max_rel"] <= max(1e-10, 8 * floor[case]["max_rel"])
+    assert c["median_rel"] < 2e-14
+    st = s.stats()
+    nm = 3 if em else 1
+    assert st["integrals"] == s.npoints * (s.npoints - 1) // 2 * nm
+    if not em:
+        assert np.array_equal(A, A.T)
+        assert np.all(np.diag(A) == 1.0 + 1.0 / s.params.tau)
+
+
+@pytest.mark.parametrize("case,omega", [("c1_n64", -0.3 + 0.9j), ("c1_n64", 1.7 - 0.05j),
+                                        ("c3_n32", -0.2 + 0.4j), ("c1_em_n64", 0.5 + 0.3j)])
+def test_assembly_matches_oracle_at_other_omega(case, omega, native_lib):
+    import oracle_lib as O
+    inp = Input(cases.input_path(case))
+    p, n = inp.params()
+    eta, g, bi = inp.tables()
+    s = EigenSolver.from_input(inp)
+    A = s.matrixAssembler(omega)
+    ref, ost = O.assemble(cases.oracle_params(p), eta, g, bi, p.dx, omega)
+    c = parity.assert_parity(A, ref, em=p.beta_e != 0, label=f"{case}@{omega}")
+    report(f"{case}@{omega}", c)
+    # identical adaptive trees: same number of integrand evaluations as the oracle
+    assert s.stats()["evals"] == ost["evals"]
+
+
+@pytest.mark.parametrize("case", ["c1", "c3"])
+def test_full_size_rows_and_properties(case, golden, native_lib):
+    """BASELINE configs at their real size (N=1024): selected rows against the reference dump,
+    plus size-independent properties (symmetry structure, diagonal, column sums, norm)."""
+    z = np.load(cases.GOLD / f"rows_{case}.npz")
+    inp = Input(cases.input_path(case))
+    s = EigenSolver.from_input(inp)
+    w = complex(*golden["assemble"][case]["omega"])
+    A = s.matrixAssembler(w)
+    st = s.stats()
+    n, dim = s.npoints, s.dim
+    em = dim != n
+    rows = z["rows"]
+    sub = A[rows]
+    ref = z["data"]
+    d = np.abs(sub - ref)
+    mag = np.abs(ref)
+    scale = float(z["maxabs"])
+    rel = np.where(mag > 0, d / np.where(mag > 0, mag, 1), 0)
+    print(f"\n[parity] {case} rows: max_rel={rel.max():.3e} median_rel={np.median(rel[mag > 0]):.3e} "
+          f"strict_frac={(d <= 1e-10 * mag).mean():.6f} max_abs/max|A|={d.max() / scale:.3e} "
+          f"assemble_ms={st['assemble_ms']:.2f} evals={st['evals']} stats={st}")
+    assert (d <= 1e-10 * mag + parity.EPS * scale).all()
+    assert (d <= 1e-10 * mag).mean() >= 0.99
+    assert rel.max() < 1e-8
+    assert np.allclose(np.diag(A), z["diag"], rtol=0, atol=0)
+    assert abs(np.linalg.norm(A) - float(z["fro"])) <= 1e-13 * float(z["fro"])
+    assert np.abs(A.sum(axis=0) - z["colsum"]).max() <= 1e-11 * scale
+    if not em:
+        assert np.array_equal(A, A.T)
+    else:
+        # block structure of include/solver.h:476-504
+        a00, a01, a10, a11 = A[:n, :n], A[:n, n:], A[n:, :n], A[n:, n:]
+        assert np.array_equal(a00, a00.T) and np.array_equal(a11, a11.T)
+        assert np.array_equal(a01, -a01.T) and np.array_equal(a10, a01.T)
+
+
+def test_sharded_assembly_sums_to_full(native_lib):
+    """Multi-GPU building block: P shards of the work items, each into a zeroed buffer, sum to
+    the single-launch matrix bit-for-bit (the shards are disjoint entries)."""
+    import torch
+    inp = Input(cases.input_path("c1_em_n64"))
+    s = EigenSolver.from_input(inp)
+    w = -0.8 + 0.25j
+    full = s.matrixAssembler(w)
+    acc = np.zeros_like(full)
+    P = 3
+    for r in range(P):
+        buf = torch.zeros((s.dim, s.dim), dtype=torch.complex128, device="cuda")
+        torch.cuda.synchronize()       # the handle launches on its own non-blocking stream
+        s.assemble_device(w, buf.data_ptr(), r, P)
+        acc += buf.cpu().numpy()
+    assert np.array_equal(acc, full)
+
+
+def test_deep_stack_spills_to_global(native_lib):
+    """Tight tolerances force deep bisection: the interval stack must follow the reference's
+    contract (depth <= integration_iteration_limit), past the shared-memory slots."""
+    import oracle_lib as O
+    txt = cases.input_path("c1_n32").read_text()
+    txt = txt.replace('"integration_precision": 1.0e-6', '"integration_precision": 1.0e-13')
+    txt = txt.replace('"integration_accuracy": 1.0e-6', '"integration_accuracy": 1.0e-15')
+    inp = Input(text=txt)
+    p, n = inp.params()
+    eta, g, bi = inp.tables()
+    s = EigenSolver.from_input(inp)
+    A = s.matrixAssembler(-0.8 + 0.25j)
+    ref, ost = O.assemble(cases.oracle_params(p), eta, g, bi, p.dx, -0.8 + 0.25j)
+    st = s.stats()
+    print("\n[deep]", st, ost)
+    c = parity.compare(A, ref)
+    assert c["max_abs_over_max"] < 1e-13
+    assert st["max_stack"] >= 8

@@ -1,0 +1,80 @@
+"""-m gpu: kernel 2 (dense step) and the Newton/secant iterate sequence against the reference."""
+import numpy as np
+import pytest
+
+import cases
+from emme_b200 import EigenSolver, Input, solve_once_eigen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dim", [7, 32, 33, 100, 256, 257, 640])
+def test_trace_delta_matches_numpy(dim, native_lib):
+    """delta = -1/trace(A^-1 A') on random, badly row-scaled complex matrices that need pivoting."""
+    rng = np.random.default_rng(dim)
+    A = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    A[::3] *= 1e-3                     # forces row interchanges
+    A[0, 0] = 0.0                      # zero leading pivot
+    B = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    inp = Input(cases.input_path("c1_n32"))
+    p, _ = inp.params()
+    n = dim
+    s = EigenSolver(p, n, np.linspace(-1, 1, n), np.zeros(n), np.ones(n))
+    d = s.trace_delta(A, B)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    assert abs(d - ref) <= 1e-10 * abs(ref), (d, ref)
+
+
+def test_trace_delta_matches_oracle_on_real_matrices(golden, native_lib):
+    import oracle_lib as O
+    inp = Input(cases.input_path("c1_n128"))
+    s = EigenSolver.from_input(inp)
+    A = cases.ref_matrix("c1_n128")
+    A2 = s.matrixAssembler(-0.79 + 0.251j)
+    Ad = (A - A2) / (0.01 - 0.001j)
+    d = s.trace_delta(A, Ad)
+    ref, info = O.trace_step(A, Ad)
+    assert info == 0
+    assert abs(d - ref) <= 1e-12 * abs(ref), (d, ref)
+
+
+def test_singular_matrix_reports_info(native_lib):
+    from emme_b200 import EmmeError
+    inp = Input(cases.input_path("c1_n32"))
+    p, _ = inp.params()
+    n = 64
+    s = EigenSolver(p, n, np.linspace(-1, 1, n), np.zeros(n), np.ones(n))
+    A = np.eye(n, dtype=np.complex128)
+    A[10] = 0
+    with pytest.raises(EmmeError, match="Linear solve failed") as ei:
+        s.trace_delta(A, np.eye(n, dtype=np.complex128))
+    assert ei.value.code == 11
+
+
+@pytest.mark.parametrize("case", ["c1_n64", "c1_n128", "c1_gk31_n128", "c1_em_n64", "c1_pos_n64", "c1", "c3"])
+def test_newton_iterates_match_reference(case, golden, native_lib):
+    """Same seeds, same step formula, same stop rule (include/solver.h:396-415,113-160;
+    src/main.cpp:43-57): every iterate and the converged omega within 1e-8 relative."""
+    rec = golden["newton"][case]
+    inp = Input(cases.input_path(case))
+    w0 = inp.initial_guess()
+    w, iters, s = solve_once_eigen(inp, w0)
+    print(f"\n[newton] {case}: {len(iters)} iterates, omega={w!r}, ref={rec['final']}, stats={s.stats()}")
+    assert len(iters) == len(rec["iterates"]) == rec["final"][2]
+    worst = 0.0
+    for (wi, di), r in zip(iters, rec["iterates"]):
+        rw = complex(r[0], r[1])
+        worst = max(worst, abs(wi - rw) / abs(rw))
+    print(f"[newton] {case}: worst iterate rel err {worst:.3e}")
+    assert worst <= 1e-8
+    rf = complex(rec["final"][0], rec["final"][1])
+    assert abs(w - rf) <= 1e-8 * abs(rf)
+
+
+def test_step_before_seed_is_an_error(native_lib):
+    from emme_b200 import EmmeError, capi
+    inp = Input(cases.input_path("c1_n32"))
+    s = EigenSolver.from_input(inp)
+    with pytest.raises(EmmeError) as ei:
+        s.newtonTraceSecantIteration()
+    assert ei.value.code == capi.E_STATE
