@@ -11,8 +11,9 @@ times larger cancel.  The checker therefore reports three things and asserts all
   * floor   : every entry satisfies |d| <= rtol*|a| + eps_floor*max|A_block|
               with eps_floor = 2^-52 -- one ulp of the block's largest entry, below which no
               consumer of A (the LU solve) can see a difference
-  * flips   : no entry is off by more than flip_rtol (a changed accept/bisect decision of the
-              adaptive quadrature moves an entry by ~1e-7 absolute)
+  * flips   : no entry is off by more than 1e-8*|a| + 64 ulp(max|A_block|) (a changed
+              accept/bisect decision of the adaptive quadrature moves an entry by ~1e-7
+              absolute)
 """
 import numpy as np
 
@@ -40,6 +41,7 @@ def compare(A, ref, em=False, rtol=1e-10):
         out["entries"] += int(d.size)
         out["strict_ok"] += int((d <= rtol * mag).sum())
         out["floor_viol"] += int((d > rtol * mag + EPS * scale).sum())
+        out["flips"] = out.get("flips", 0) + int((d > 1e-8 * mag + 64 * EPS * scale).sum())
         out["max_rel"] = max(out["max_rel"], float(rel.max()))
         out["max_abs"] = max(out["max_abs"], float(d.max()))
         if scale > 0:
@@ -52,12 +54,12 @@ def compare(A, ref, em=False, rtol=1e-10):
     return out
 
 
-def assert_parity(A, ref, em=False, rtol=1e-10, min_strict=0.95, label=""):
+def assert_parity(A, ref, em=False, rtol=1e-10, min_strict=0.90, label=""):
     assert A.shape == ref.shape
     assert np.isfinite(A.view(np.float64)).all(), f"{label}: non-finite entries"
     c = compare(A, ref, em=em, rtol=rtol)
     msg = f"{label}: {c}"
     assert c["floor_viol"] == 0, "entries beyond rtol*|a| + ulp(max|A|): " + msg
     assert c["strict_frac"] >= min_strict, "too few entries within strict rtol: " + msg
-    assert c["max_rel"] < 1e-8, "adaptive-tree flip suspected: " + msg
+    assert c["flips"] == 0, "adaptive-tree flip suspected: " + msg
     return c
