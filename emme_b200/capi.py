@@ -28,7 +28,7 @@ class EmmeStats(C.Structure):
     """struct emme_stats"""
     _fields_ = [(n, C.c_ulonglong) for n in
                 ("integrals", "panels", "evals", "fwd_trips", "bwd_trips", "max_stack")] + [
-        ("assemble_ms", C.c_double), ("dense_ms", C.c_double)]
+        ("assemble_ms", C.c_double), ("dense_ms", C.c_double), ("launches", C.c_ulonglong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -44,6 +44,9 @@ PROTOTYPES = {
     "emme_create": (C.c_int, [C.POINTER(EmmeParams), C.c_int, _dp, _dp, _dp, C.c_int, C.POINTER(_vp)]),
     "emme_destroy": (C.c_int, [_vp]),
     "emme_dim": (C.c_int, [_vp]),
+    "emme_set_tables": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "emme_set_params": (C.c_int, [_vp, C.POINTER(EmmeParams)]),
+    "emme_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
     "emme_assemble": (C.c_int, [_vp, C.c_double, C.c_double, _vp]),
     "emme_assemble_device": (C.c_int, [_vp, C.c_double, C.c_double, _vp, C.c_int, C.c_int]),
     "emme_seed": (C.c_int, [_vp, C.c_double, C.c_double]),

@@ -272,7 +272,8 @@ int assembly_stack_smem() { return STACK_SMEM; }
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
                             const double* bi, void* A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
-                            unsigned long long* stats, int grid_blocks, cudaStream_t stream) {
+                            unsigned long long* stats, int grid_blocks, cudaStream_t stream,
+                            unsigned long long* n_launches) {
     const unsigned long long N = rc.N;
     const unsigned long long n_items = N * (N - 1) / 2 * (rc.em ? 3ULL : 1ULL);
     const unsigned long long sc = shard_count, si = shard_index;
@@ -283,8 +284,10 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
     if (e != cudaSuccess) return e;
     if (shard_index == 0) {
         diagonal_kernel<<<(rc.N + 127) / 128, 128, 0, stream>>>(rc, bi, (double2*)A);
+        if (n_launches) ++*n_launches;
     }
     if (n_local > 0) {
+        if (n_launches) ++*n_launches;
         if (rc.order == 15) {
             assemble_kernel<15><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,

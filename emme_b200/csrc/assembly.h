@@ -16,5 +16,6 @@ int assembly_stack_smem();
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
                             const double* bi, void* A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
-                            unsigned long long* stats, int grid_blocks, cudaStream_t stream);
+                            unsigned long long* stats, int grid_blocks, cudaStream_t stream,
+                            unsigned long long* n_launches);
 }  // namespace emme

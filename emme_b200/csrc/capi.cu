@@ -55,6 +55,7 @@ struct emme_solver {
     zc w{0, 0}, dw{0, 0};
     int shard_index = 0, shard_count = 1;
     emme_stats stats{};
+    unsigned long long launches = 0;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
 };
 
@@ -73,6 +74,44 @@ int emme_device_count(void) {
 }
 
 int emme_dim(const emme_solver* s) { return s ? s->dim : -1; }
+
+int emme_fp64_peak(int device, double* tflops, double* sm_mhz_nominal) {
+    if (!tflops) return fail(-2, "null output");
+    if (emme_device_count() <= 0) return fail(EMME_E_NO_DEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    CU(emme::measure_fp64_peak(tflops));
+    if (sm_mhz_nominal) {
+        int khz = 0;
+        CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+        *sm_mhz_nominal = khz / 1000.0;
+    }
+    return 0;
+}
+
+int emme_set_tables(emme_solver* s, const double* eta, const double* g, const double* bi) {
+    if (!s) return fail(-1, "null handle");
+    if (!eta) return fail(-2, "null eta");
+    if (!g) return fail(-3, "null g");
+    if (!bi) return fail(-4, "null bi");
+    CU(cudaSetDevice(s->device));
+    const size_t tb = sizeof(double) * s->N;
+    CU(cudaMemcpyAsync(s->d_eta, eta, tb, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_g, g, tb, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_bi, bi, tb, cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+int emme_set_params(emme_solver* s, const emme_params* p) {
+    if (!s) return fail(-1, "null handle");
+    if (!p) return fail(-2, "null params");
+    const int dim = std::fpclassify(p->beta_e) == FP_ZERO ? s->N : 2 * s->N;
+    if (dim != s->dim) return fail(-2, "emme_set_params: beta_e changes the matrix dimension");
+    if (p->integration_start_points != s->p.integration_start_points ||
+        p->integration_iteration_limit != s->p.integration_iteration_limit)
+        return fail(-2, "emme_set_params: quadrature order / depth must not change");
+    s->p = *p;
+    return 0;
+}
 
 int emme_destroy(emme_solver* s) {
     if (!s) return 0;
@@ -159,7 +198,7 @@ static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, in
     CU(cudaEventRecord(s->ev0, s->stream));
     CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, dst, shard_index, shard_count,
                              s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->grid_blocks,
-                             s->stream));
+                             s->stream, &s->launches));
     CU(cudaEventRecord(s->ev1, s->stream));
     return 0;
 }
@@ -210,7 +249,7 @@ static int dense_delta(emme_solver* s, zc* delta) {
     CU(cudaEventRecord(e0, s->stream));
     CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
     CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
-                                s->stream));
+                                s->stream, &s->launches));
     CU(cudaEventRecord(e1, s->stream));
     double tr[2];
     int info = 0;
@@ -237,6 +276,7 @@ static int dense_delta(emme_solver* s, zc* delta) {
 static int secant(emme_solver* s) {
     CU(emme::launch_secant(s->A, s->Aold, s->Ad, (size_t)s->dim * s->dim, s->dw.real(),
                            s->dw.imag(), s->sms, s->stream));
+    ++s->launches;
     return 0;
 }
 
@@ -375,6 +415,7 @@ int emme_get_stats(const emme_solver* s, emme_stats* out) {
     if (!s) return fail(-1, "null handle");
     if (!out) return fail(-2, "null output");
     *out = s->stats;
+    out->launches = s->launches;
     return 0;
 }
 

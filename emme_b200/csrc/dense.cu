@@ -364,6 +364,51 @@ cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, d
     return cudaGetLastError();
 }
 
+// ---- FP64 FMA peak: 8 independent DFMA chains per thread, registers only ----
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+cudaError_t measure_fp64_peak(double* tflops) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, iters = 4096;
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(double) * blocks * 256);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, 256>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8 * 16 * (double)iters * blocks * 256;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError();
+}
+
 size_t dense_workspace_bytes(int dim) {
     const int nblk = (dim + PT - 1) / PT;
     return sizeof(PanelCand) * 2 * (size_t)nblk + sizeof(int) * (size_t)dim + 64;
@@ -371,7 +416,8 @@ size_t dense_workspace_bytes(int dim) {
 
 // W (dim x dim, destroyed) and B (dim x dim, destroyed): trace(W^-1 B) -> *d_trace (device).
 cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, void* d_trace,
-                               int* d_info, cudaStream_t stream) {
+                               int* d_info, cudaStream_t stream, unsigned long long* n_launches) {
+    unsigned long long nl = 0;
     z_t* W = (z_t*)Wv;
     z_t* B = (z_t*)Bv;
     const int ld = dim;
@@ -388,10 +434,12 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
         void* args[] = {&W, (void*)&ld, &dim, &k0, &jb, &ipiv, &xchg, &d_info};
         e = cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(nblk), dim3(PT), args, 0, stream);
         if (e != cudaSuccess) return e;
+        nl += 2;
         const int ncol = (dim - (k0 + jb)) + dim;
         swap_trsm_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(W, B, ld, dim, k0, jb, ipiv);
         const int M = dim - (k0 + jb);
         if (M > 0) {
+            nl += 2;
             // trailing W
             dim3 g1((M + GN - 1) / GN, (M + GM - 1) / GM);
             zgemm_sub_kernel<<<g1, 256, 0, stream>>>(W + (size_t)(k0 + jb) * ld + (k0 + jb), ld,
@@ -410,13 +458,16 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
         const int jb = dim - k0 < NB ? dim - k0 : NB;
         const int ncols = k0 + jb;   // columns c <= last row of this block
         utrsm_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(W, B, ld, k0, jb, ncols);
+        nl += 1;
         if (k0 > 0) {
+            nl += 1;
             dim3 g((k0 + GN - 1) / GN, (k0 + GM - 1) / GM);
             zgemm_sub_kernel<<<g, 256, 0, stream>>>(B, ld, W + k0, ld, B + (size_t)k0 * ld, ld, k0,
                                                     k0, jb);
         }
     }
     trace_kernel<<<1, 256, 0, stream>>>(B, ld, dim, (z_t*)d_trace);
+    if (n_launches) *n_launches += nl + 1;
     return cudaGetLastError();
 }
 

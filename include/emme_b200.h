@@ -57,12 +57,17 @@ typedef struct emme_stats {
     unsigned long long max_stack; /* deepest interval stack seen                   */
     double assemble_ms;           /* CUDA-event time of the last assembly kernel    */
     double dense_ms;              /* CUDA-event time of the last dense step         */
+    unsigned long long launches;  /* kernels launched by this handle since creation */
 } emme_stats;
 
 typedef struct emme_solver emme_solver; /* opaque; owns device memory */
 
 /* ---- device / library ---- */
 int emme_device_count(void);
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (a register-resident DFMA chain
+ * kernel, the denominator of the assembly kernel's roofline; MEASURED_PEAKS.json has no
+ * FP64 figure).  Returns 0 on success. */
+int emme_fp64_peak(int device, double* tflops, double* sm_mhz_nominal);
 const char* emme_last_error(void);
 const char* emme_version(void);
 
@@ -77,6 +82,11 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
                 const double* bi, int device, emme_solver** out);
 int emme_destroy(emme_solver* s);
 int emme_dim(const emme_solver* s);
+/* Replace the per-node tables (a scan over shat, k_rho, ... changes g and bi but not the
+ * mesh size): asynchronous host-to-device copies on the handle's stream. */
+int emme_set_tables(emme_solver* s, const double* eta, const double* g, const double* bi);
+/* Replace the scalar parameters (npoints and the EM/ES kind must not change). */
+int emme_set_params(emme_solver* s, const emme_params* p);
 
 /* ---- A(omega): EigenSolver::matrixAssembler (include/solver.h:417-515) ---------------
  * emme_assemble        : into caller's HOST buffer (dim*dim complex128, row-major).

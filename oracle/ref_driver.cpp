@@ -27,6 +27,10 @@
 //   time_newton <input.json>
 //       wall time of ctor (2 assemblies) and of ONE newtonTraceSecantIteration
 //       split into zsysv / assembly as the reference's own Timer records them.
+//   time_dense <n> [reps]
+//       the LAPACK call of newtonTraceSecantIteration (include/solver.h:130-136: zsysv,
+//       'U', n right-hand sides, lwork = n*n) on a synthetic complex-symmetric n x n system,
+//       for the CPU baseline of the dense step at sizes whose assembly is too slow to run.
 //   kat
 //       known-answer values of the leaf numerics (Gauss-Kronrod, Bessel helper,
 //       SingularityHandler, Grid) as JSON.
@@ -237,6 +241,40 @@ static int mode_time_newton(int argc, char** argv) {
     return 0;
 }
 
+static int mode_time_dense(int argc, char** argv) {
+    if (argc < 3) return 64;
+    const lapack_int n = std::atoi(argv[2]);
+    const int reps = argc > 3 ? std::atoi(argv[3]) : 1;
+    Matrix<cplx> A(n, n), B(n, n);
+    double best = 1e300;
+    for (int rep = 0; rep < reps; ++rep) {
+        unsigned long long st = 88172645463325252ull;
+        auto rnd = [&]() {
+            st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+            return (double)(st >> 11) / 9007199254740992.0 - 0.5;
+        };
+        for (lapack_int i = 0; i < n; ++i)
+            for (lapack_int j = i; j < n; ++j) {
+                cplx v(rnd() * 0.05, rnd() * 0.05), w(rnd(), rnd());
+                if (i == j) v += 2.0;
+                A(i, j) = A(j, i) = v;
+                B(i, j) = B(j, i) = w;
+            }
+        lapack_int work_length = n * n, info = 0;
+        std::vector<cplx> work(work_length);
+        std::vector<lapack_int> ipiv(n);
+        auto t0 = clk::now();
+        LAPACK_zsysv("Upper", &n, &n, A.data(), &n, ipiv.data(), B.data(), &n, work.data(),
+                     &work_length, &info);
+        auto t1 = clk::now();
+        if (info != 0) { std::printf("ERROR zsysv info %d\n", info); return 1; }
+        best = std::min(best, secs(t0, t1));
+    }
+    std::printf("{\"n\": %d, \"zsysv_s\": %.6f, \"threads\": %u}\n", n, best,
+                std::thread::hardware_concurrency());
+    return 0;
+}
+
 static void print_c(const char* name, cplx v, bool last = false) {
     std::printf("  \"%s\": [%.17g, %.17g]%s\n", name, v.real(), v.imag(), last ? "" : ",");
 }
@@ -288,7 +326,7 @@ static int mode_kat() {
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        std::fprintf(stderr, "usage: %s assemble|newton|kappa|tables|time_rows|time_newton|kat ...\n", argv[0]);
+        std::fprintf(stderr, "usage: %s assemble|newton|kappa|tables|time_rows|time_newton|time_dense|kat ...\n", argv[0]);
         return 64;
     }
     try {
@@ -299,6 +337,7 @@ int main(int argc, char** argv) {
         if (m == "tables") return mode_tables(argc, argv);
         if (m == "time_rows") return mode_time_rows(argc, argv);
         if (m == "time_newton") return mode_time_newton(argc, argv);
+        if (m == "time_dense") return mode_time_dense(argc, argv);
         if (m == "kat") return mode_kat();
     } catch (const std::exception& e) {
         std::printf("ERROR %s\n", e.what());
