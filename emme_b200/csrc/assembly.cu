@@ -1,4 +1,4 @@
-// assembly.cu -- kernel 1: warp-cooperative adaptive Gauss-Kronrod assembly of A(omega).
+// assembly.cu -- kernel 1: adaptive Gauss-Kronrod assembly of A(omega), one lane per quadrature.
 //
 // Replaces EigenSolver::matrixAssembler (reference include/solver.h:417-515) together with
 // everything it calls per matrix element: Parameters::kappa_f_tau / kappa_f_tau_e
@@ -6,20 +6,23 @@
 // (include/functions.h:181-251,305-331), util::bessel_i_alter_helper (:381-408),
 // SingularityHandler (src/singularity_handler.cpp:3-24) and the DedicatedThreadPool fan-out.
 //
-// Mapping:
-//   * a work item is one adaptive quadrature: (pair i<j, mode m); pairs are enumerated
-//     diagonal-major (d = j-i ascending) so that neighbouring items cost about the same and
-//     the most expensive ones (small d) are issued first;
-//   * a GROUP of GS lanes owns one item at a time: GS = 16 for GK15 (two groups per warp),
-//     GS = 32 for GK31; lane g evaluates Kronrod node g of the current panel;
-//   * the panel sums are accumulated in the reference's order (centre, then +-a_1, +-a_2 ...)
-//     by broadcasting each lane's weighted value with warp shuffles, so every lane of the
-//     group holds identical K, G and takes identical accept/bisect decisions;
-//   * the LIFO interval stack of gauss_kronrod_adaptive lives in shared memory (one slot
-//     array per group, leader-owned), spilling to global memory beyond STACK_SMEM entries so
-//     that the contract "depth <= integration_iteration_limit" holds for any input;
-//   * the grid is persistent (SM count x resident CTAs); groups pull items from a global
-//     atomic counter and refill independently, so a group never waits for its warp sibling.
+// Mapping (round-1 profile r1a motivated the change from "lane = node"):
+//   * a work item is one adaptive quadrature (pair i<j, mode m); items are ordered mode-major,
+//     pairs diagonal-major (d = j-i ascending), so consecutive items are near-identical
+//     integrals (same |i-j|, neighbouring eta) and the most expensive ones run first;
+//   * a LANE owns one item and walks its panels; the 32 lanes of a warp walk the 15 (31)
+//     Kronrod nodes of their current panels in lockstep (node index j is warp-uniform), so
+//     - the Miller recurrences of neighbouring integrals at the same node have nearly the
+//       same trip count (little divergence),
+//     - the exp(<-40) underflow guard skips the Bessel part for the whole warp at once,
+//     - the panel sums are accumulated sequentially in the reference's own order (centre,
+//       then f(+a_i)+f(-a_i), i = 1..) with no shuffles;
+//   * the LIFO interval stack of gauss_kronrod_adaptive is per lane: the left child stays in
+//     registers, right siblings go to shared memory and, past STACK_SMEM entries, to a global
+//     spill area sized for the contract "depth <= integration_iteration_limit";
+//   * persistent grid; at every panel boundary the idle lanes of a warp (finished integrals)
+//     refill TOGETHER from a global atomic counter once at least `refill_min` of them are idle,
+//     so a warp always consists of a few cohorts of consecutive items.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,15 +35,13 @@ namespace emme {
 __constant__ GKTables c_gk15 = EMME_GK15_INIT;
 __constant__ GKTables c_gk31 = EMME_GK31_INIT;
 
-constexpr int STACK_SMEM = 24;  // interval-stack entries kept in shared memory per group
+constexpr int STACK_SMEM = 8;    // right-sibling intervals kept in shared memory per lane
 constexpr int BLOCK = 128;
+constexpr int MIN_BLOCKS = 4;
 
-// item k (local to this shard) -> global item, pair (i, j) and mode m.
+// pair index p (diagonal-major: d = j-i ascending, i ascending) -> (i, j).
 // pairs with diagonal < d: T(d) = (d-1)*(2N-d)/2
-__device__ __forceinline__ void decode_item(unsigned long long kg, int N, int nm, int& i, int& j,
-                                            int& m) {
-    const unsigned long long p = kg / (unsigned)nm;
-    m = (int)(kg - p * (unsigned)nm);
+__device__ __forceinline__ void decode_pair(unsigned long long p, int N, int& i, int& j) {
     const double tn = 2.0 * N + 1.0;
     double disc = tn * tn - 8.0 * ((double)N + (double)p);
     if (disc < 0.) disc = 0.;
@@ -85,99 +86,98 @@ __device__ __forceinline__ void scatter(const RunConst& rc, double2* A, int i, i
 }
 
 template <int ORDER>
-__global__ void __launch_bounds__(BLOCK, 4)
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double* __restrict__ gt,
                 const double* __restrict__ bt, double2* __restrict__ A,
                 unsigned long long n_items_local, unsigned long long shard_index,
                 unsigned long long shard_count, unsigned long long* __restrict__ counter,
-                double2* __restrict__ spill, int spill_cap, unsigned long long* __restrict__ stats) {
-    constexpr int GS = ORDER == 15 ? 16 : 32;   // lanes per group
+                double2* __restrict__ spill, int spill_cap, unsigned long long* __restrict__ stats,
+                int refill_min) {
     constexpr int H = (ORDER - 1) / 2;          // 7 or 15 symmetric node pairs
-    constexpr int GPB = BLOCK / GS;             // groups per block
     const GKTables& T = ORDER == 15 ? c_gk15 : c_gk31;
 
-    __shared__ double2 s_stack[GPB][STACK_SMEM];
+    __shared__ double2 s_stack[STACK_SMEM][BLOCK];   // [slot][thread]: conflict-free
 
     const int lane = threadIdx.x & 31;
-    const int gl = lane & (GS - 1);             // lane within group
-    const int grp = threadIdx.x / GS;           // group within block
-    const unsigned gmask = GS == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+    const unsigned lt_mask = (1u << lane) - 1u;
     double2* my_spill =
-        spill ? spill + ((size_t)blockIdx.x * GPB + grp) * (size_t)spill_cap : nullptr;
+        spill ? spill + ((size_t)blockIdx.x * BLOCK + threadIdx.x) * (size_t)spill_cap : nullptr;
 
-    // node owned by this lane: 0 centre, 1..H -> +a, H+1..2H -> -a; spare lane mirrors centre
-    int nidx = gl == 0 ? 0 : (gl <= H ? gl : (gl <= 2 * H ? gl - H : 0));
-    const double node = gl <= H ? T.a[nidx] : -T.a[nidx];
-    const double kw = T.kw[nidx];
-    const double gw = T.gw[nidx];
-    const bool counted = gl <= 2 * H;
-
-    const int nm = rc.em ? 3 : 1;
-    bool active = false, exhausted = false;
+    const unsigned long long n_pairs = (unsigned long long)rc.N * (rc.N - 1) / 2;
+    bool active = false;
+    bool warp_exhausted = false;
     int it_i = 0, it_j = 0, it_m = 0, top = 0;
     PairConst pc;
     cplx sum = mk(0., 0.);
-    double abs_tol = 0.;
+    double abs_tol = 0., l = 0., r = 0.;
     EvalCounters cnt{0u, 0u};
-    unsigned long long n_eval = 0, n_panel = 0, n_int = 0, n_fwd = 0, n_bwd = 0;
+    unsigned long long n_eval = 0, n_panel = 0, n_int = 0;
     int max_top = 0;
 
     for (;;) {
-        if (!active && !exhausted) {
-            unsigned long long k = 0;
-            if (gl == 0) k = atomicAdd(counter, 1ULL);
-            k = __shfl_sync(gmask, k, 0, GS);
-            if (k >= n_items_local) {
-                exhausted = true;
-            } else {
-                decode_item(k * shard_count + shard_index, rc.N, nm, it_i, it_j, it_m);
-                pc = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
-                sum = mk(0., 0.);
-                abs_tol = 0.;
-                if (gl == 0) s_stack[grp][0] = make_double2(0.0, rc.half_pi);
-                top = 1;
-                active = true;
-            }
-        }
-        if (__all_sync(0xffffffffu, !active)) break;
-        if (active) {
-            // ---- pop (leader) and broadcast ----
-            --top;
-            double l = 0., r = 0.;
-            if (gl == 0) {
-                const double2 e = top < STACK_SMEM ? s_stack[grp][top] : my_spill[top - STACK_SMEM];
-                l = e.x;
-                r = e.y;
-            }
-            l = __shfl_sync(gmask, l, 0, GS);
-            r = __shfl_sync(gmask, r, 0, GS);
-            const double mid = (r + l) / 2;
-            const double scale = (r - l) / 2;
-            // node position exactly as the reference forms it: scale*x + mid, no FMA
-            const double x = __dadd_rn(__dmul_rn(scale, node), mid);
-            const cplx fx = eval_node(rc, pc, it_m, x, cnt);
-            if (counted) ++n_eval;
-            // f(+a_i) + f(-a_i) on lanes 1..H
-            cplx f = fx;
-            {
-                const double pr = __shfl_down_sync(gmask, fx.re, H, GS);
-                const double pi = __shfl_down_sync(gmask, fx.im, H, GS);
-                if (gl >= 1 && gl <= H) f = mk(fx.re + pr, fx.im + pi);
-            }
-            const cplx kf = mk(kw * f.re, kw * f.im);
-            const cplx gf = mk(gw * f.re, gw * f.im);
-            // sequential sums in node order (include/functions.h:189-201)
-            cplx K = mk(__shfl_sync(gmask, kf.re, 0, GS), __shfl_sync(gmask, kf.im, 0, GS));
-            cplx G = mk(__shfl_sync(gmask, gf.re, 0, GS), __shfl_sync(gmask, gf.im, 0, GS));
-#pragma unroll
-            for (int n = 1; n <= H; ++n) {
-                K.re += __shfl_sync(gmask, kf.re, n, GS);
-                K.im += __shfl_sync(gmask, kf.im, n, GS);
-                if ((n & 1) == 0) {
-                    G.re += __shfl_sync(gmask, gf.re, n, GS);
-                    G.im += __shfl_sync(gmask, gf.im, n, GS);
+        // ---- refill: idle lanes fetch consecutive items together ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !warp_exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            bool miss = false;
+            if (!active) {
+                const unsigned long long k = base + (unsigned)__popc(idle & lt_mask);
+                if (k >= n_items_local) {
+                    miss = true;
+                } else {
+                    // shards take chunks of 32 consecutive items round-robin
+                    const unsigned long long kg = (k >> 5) * (shard_count << 5) + (shard_index << 5) + (k & 31);
+                    it_m = (int)(kg / n_pairs);
+                    decode_pair(kg - (unsigned long long)it_m * n_pairs, rc.N, it_i, it_j);
+                    pc = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
+                    sum = mk(0., 0.);
+                    abs_tol = 0.;
+                    l = 0.0;
+                    r = rc.half_pi;
+                    top = 0;
+                    active = true;
                 }
             }
+            if (__any_sync(0xffffffffu, miss)) warp_exhausted = true;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (warp_exhausted) break;
+            continue;
+        }
+        // ---- one Gauss-Kronrod panel per active lane, nodes in lockstep ----
+        const double mid = (r + l) / 2;
+        const double scale = (r - l) / 2;
+        cplx K = mk(0., 0.), G = mk(0., 0.), fplus = mk(0., 0.);
+#pragma unroll 1
+        for (int j = 0; j <= 2 * H; ++j) {
+            const int ni = (j + 1) >> 1;                       // node index 0..H
+            const double node = (j & 1) ? T.a[ni] : -T.a[ni];  // j = 0: -0*scale + mid = mid
+            if (active) {
+                // node position exactly as the reference forms it: scale*x + mid, no FMA
+                const double x = __dadd_rn(__dmul_rn(scale, node), mid);
+                const cplx fx = eval_node(rc, pc, it_m, x, cnt);
+                ++n_eval;
+                if (j == 0) {
+                    K = mk(T.kw[0] * fx.re, T.kw[0] * fx.im);
+                    G = mk(T.gw[0] * fx.re, T.gw[0] * fx.im);
+                } else if (j & 1) {
+                    fplus = fx;
+                } else {
+                    const cplx f = mk(fplus.re + fx.re, fplus.im + fx.im);
+                    const double kw = T.kw[ni], gw = T.gw[ni];
+                    if ((ni & 1) == 0) {
+                        G.re += gw * f.re;
+                        G.im += gw * f.im;
+                    }
+                    K.re += kw * f.re;
+                    K.im += kw * f.im;
+                }
+            }
+        }
+        if (active) {
             ++n_panel;
             // ---- accept / bisect (include/functions.h:233-247) ----
             const cplx integral = mk(K.re * scale, K.im * scale);
@@ -189,32 +189,32 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
             const bool split = ldexp(scale, rc.maxdepth) > rc.thr_len &&
                                err > abs_tol * rc.inv_scale + rc.prec && err > rel + rc.prec;
             if (split) {
-                if (gl == 0) {
-                    const double2 e1 = make_double2(mid, r), e2 = make_double2(l, mid);
-                    if (top < STACK_SMEM) s_stack[grp][top] = e1; else my_spill[top - STACK_SMEM] = e1;
-                    if (top + 1 < STACK_SMEM) s_stack[grp][top + 1] = e2; else my_spill[top + 1 - STACK_SMEM] = e2;
-                }
-                top += 2;
+                // push the right half, continue with the left half (LIFO: left is next)
+                const double2 e = make_double2(mid, r);
+                if (top < STACK_SMEM) s_stack[top][threadIdx.x] = e; else my_spill[top - STACK_SMEM] = e;
+                ++top;
                 max_top = max(max_top, top);
+                r = mid;
             } else {
                 sum = sum + integral;
-            }
-            if (top == 0) {
-                // ---- finalize: kappa = -i*pref*sum (+ electron part), scatter ----
-                if (gl == 0) {
+                if (top > 0) {
+                    --top;
+                    const double2 e = top < STACK_SMEM ? s_stack[top][threadIdx.x] : my_spill[top - STACK_SMEM];
+                    l = e.x;
+                    r = e.y;
+                } else {
+                    // ---- finalize: kappa = -i*pref*sum (+ electron part), scatter ----
                     cplx kap = mk(rc.kappa_pref * sum.im, -rc.kappa_pref * sum.re);
                     if (it_m > 0) kap = kap + kappa_e(rc, it_m, pc.deta, gt[it_i] - gt[it_j]);
                     scatter(rc, A, it_i, it_j, it_m, kap);
+                    ++n_int;
+                    active = false;
                 }
-                ++n_int;
-                active = false;
             }
         }
     }
     // ---- counters ----
-    n_fwd = counted ? cnt.fwd : 0;
-    n_bwd = counted ? cnt.bwd : 0;
-    if (gl != 0) { n_panel = 0; n_int = 0; }
+    unsigned long long n_fwd = cnt.fwd, n_bwd = cnt.bwd;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
@@ -230,7 +230,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
         atomicAdd(&stats[2], n_eval);
         atomicAdd(&stats[3], n_fwd);
         atomicAdd(&stats[4], n_bwd);
-        atomicMax(&stats[5], (unsigned long long)max_top);
+        atomicMax(&stats[5], (unsigned long long)(max_top + 1));
     }
 }
 
@@ -266,18 +266,26 @@ int assembly_grid_blocks(int order, int device) {
     return sms * g_blocks_per_sm[idx];
 }
 
-int assembly_groups_per_block(int order) { return order == 15 ? BLOCK / 16 : BLOCK / 32; }
+int assembly_groups_per_block(int order) { (void)order; return BLOCK; }  // stacks are per lane
 int assembly_stack_smem() { return STACK_SMEM; }
 
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
                             const double* bi, void* A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches) {
+                            unsigned long long* n_launches, int refill_min) {
     const unsigned long long N = rc.N;
     const unsigned long long n_items = N * (N - 1) / 2 * (rc.em ? 3ULL : 1ULL);
     const unsigned long long sc = shard_count, si = shard_index;
-    const unsigned long long n_local = n_items > si ? (n_items - si + sc - 1) / sc : 0;
+    // shards own chunks of 32 consecutive items, round-robin
+    const unsigned long long n_chunks = (n_items + 31) / 32;
+    unsigned long long n_local = 0;
+    if (n_chunks > si) {
+        const unsigned long long my_chunks = (n_chunks - si + sc - 1) / sc;
+        n_local = my_chunks * 32;
+        const unsigned long long last_chunk = (my_chunks - 1) * sc + si;   // global index
+        if (last_chunk == n_chunks - 1) n_local -= n_chunks * 32 - n_items;
+    }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
@@ -291,11 +299,11 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
         if (rc.order == 15) {
             assemble_kernel<15><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats);
+                stats, refill_min);
         } else {
             assemble_kernel<31><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats);
+                stats, refill_min);
         }
     }
     return cudaGetLastError();

@@ -12,10 +12,11 @@ int assembly_stack_smem();
 
 // Launch diagonal + quadrature kernels on `stream`.  `counter` (1 x u64), `stats` (8 x u64)
 // and `spill` (grid_blocks*groups_per_block*spill_cap double2, may be null when
-// spill_cap == 0) are device scratch owned by the handle.
+// spill_cap == 0) are device scratch owned by the handle.  refill_min: idle lanes of a warp
+// refill together once at least this many are idle (1 = per lane, 32 = whole-warp batches).
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
                             const double* bi, void* A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches);
+                            unsigned long long* n_launches, int refill_min);
 }  // namespace emme

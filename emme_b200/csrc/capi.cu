@@ -6,6 +6,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -56,6 +57,7 @@ struct emme_solver {
     int shard_index = 0, shard_count = 1;
     emme_stats stats{};
     unsigned long long launches = 0;
+    int refill_min = 16;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
 };
 
@@ -170,8 +172,11 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_stats, 8 * sizeof(unsigned long long)));
     s->grid_blocks = emme::assembly_grid_blocks(p->integration_start_points, device);
-    // interval stack: at most integration_iteration_limit + 1 live entries
-    s->spill_cap = p->integration_iteration_limit + 2 - emme::assembly_stack_smem();
+    // interval stack: at most integration_iteration_limit right siblings
+    if (const char* e = std::getenv("EMME_REFILL_MIN")) s->refill_min = std::atoi(e);
+    if (s->refill_min < 1) s->refill_min = 1;
+    if (s->refill_min > 32) s->refill_min = 32;
+    s->spill_cap = p->integration_iteration_limit + 1 - emme::assembly_stack_smem();
     if (s->spill_cap < 0) s->spill_cap = 0;
     if (s->spill_cap > 0) {
         const size_t groups = (size_t)s->grid_blocks *
@@ -198,7 +203,7 @@ static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, in
     CU(cudaEventRecord(s->ev0, s->stream));
     CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, dst, shard_index, shard_count,
                              s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->grid_blocks,
-                             s->stream, &s->launches));
+                             s->stream, &s->launches, s->refill_min));
     CU(cudaEventRecord(s->ev1, s->stream));
     return 0;
 }

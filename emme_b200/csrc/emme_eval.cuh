@@ -46,6 +46,13 @@ EMME_HD cplx recip(cplx a) {
 }
 // i*a
 EMME_HD cplx mul_i(cplx a) { return mk(-a.im, a.re); }
+EMME_HD double rsqrt_(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);   // host build (tests/emul) only
+#endif
+}
 
 // Scalars of the run (one per assembly), precomputed on the host in the reference's own
 // association order so that they are bit-identical to what the reference multiplies by.
@@ -119,32 +126,36 @@ struct EvalCounters {
 EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalCounters& cnt) {
     const double THRESHOLD = 2.e+7;
     const double az = sqrt(norm2(z));
-    int n = (int)(floor(az) + 1);
-    const int n0 = n;
+    // the order n is carried as a double (exact): no int->double conversion per trip
+    const double dn0 = floor(az) + 1.0;
+    double dn = dn0;
     // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared.
-    const double thr2 = fmax(THRESHOLD * ((double)n * sqrt(norm2(zc))), THRESHOLD * THRESHOLD);
+    const double thr2 = fmax(THRESHOLD * (dn * sqrt(norm2(zc))), THRESHOLD * THRESHOLD);
     cplx p0 = mk(0., 0.), p1 = mk(1., 0.);
     while (norm2(p1) <= thr2) {
-        const cplx c = (double)n * zc;
+        const cplx c = dn * zc;
         const cplx pt = p0 - c * p1;
         p0 = p1;
         p1 = pt;
-        ++n;
+        dn += 1.0;
     }
-    cnt.fwd += (unsigned)(n - n0);
+    cnt.fwd += (unsigned)(dn - dn0);
     y0 = recip(p1);
     y1 = mk(0., 0.);
     mu = mk(0., 0.);
+    dn -= 1.0;
+    cnt.bwd += (unsigned)dn;
+    // 2*(Re z < 0 ? 1 - 2*(n & 1) : 1): alternates with n when Re z < 0
     const bool neg = z.re < 0;
-    --n;
-    cnt.bwd += (unsigned)n;
-    for (; n > 0; --n) {
-        const cplx c = (double)n * zc;
+    const double flip = neg ? -1.0 : 1.0;
+    double sg = (neg && (((long long)dn) & 1)) ? -2.0 : 2.0;
+    for (; dn > 0.5; dn -= 1.0) {
+        const cplx c = dn * zc;
         const cplx yt = c * y0 + y1;
         y1 = y0;
         y0 = yt;
-        const double sg = neg ? (double)(2 - 4 * (n & 1)) : 2.0;
         mu = mu + sg * y1;
+        sg *= flip;
     }
     mu = mu + y0;
 }
@@ -152,16 +163,19 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
 // g(x) for mode m (0, 1, 2).  x in (0, pi/2).
 EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
                        EvalCounters& cnt) {
-    const double c = cos(x);
-    const double t = tan(x);
-    // contour rotation e = exp(-i*omi*atan(t/arc)), tau~ = t*e   (src/Parameters.cpp:121-124)
+    // t = tan x and cos x from one sincos (include/functions.h:316-317)
+    double sx, c;
+    sincos(x, &sx, &c);
+    const double t = sx / c;
+    // contour rotation e = exp(-i*omi*atan(u)), u = t/arc, tau~ = t*e (src/Parameters.cpp:121-124):
+    // cos(atan u) = 1/sqrt(1+u^2), sin(atan u) = u/sqrt(1+u^2) -- no atan, no second sincos
     const double u = t / rc.arc;
-    double sn, cs;
-    sincos(atan(u), &sn, &cs);
-    const cplx e = mk(cs, -rc.omi * sn);
+    const double w1 = 1.0 + u * u;
+    const double rs = rsqrt_(w1);
+    const cplx e = mk(rs, -rc.omi * (u * rs));
     const cplx taut = t * e;
-    // jacobian (:126-129): e - i*e*omi*t/(arc*(1+u^2))
-    const double jd = rc.omi * t / (rc.arc * (1.0 + u * u));
+    // jacobian (:126-129): e - i*e*omi*t/(arc*(1+u^2)) = e - i*e*omi*u/(1+u^2)
+    const double jd = rc.omi * u / w1;
     const cplx jacob = e - jd * mul_i(e);
     // lambda = 1 + i*cl*tau~ (:101-106, :131)
     const cplx lambda = mk(1.0 - pc.cl * taut.im, pc.cl * taut.re);
