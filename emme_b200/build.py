@@ -51,13 +51,14 @@ def _run(cmd, verbose):
     return r
 
 
-def build_library(force=False, verbose=False, extra_flags=()):
+def build_library(force=False, verbose=False, extra_flags=(), out=None, tag=""):
     srcs = CU_SOURCES + HOST_SOURCES
+    LIB = out or globals()["LIB"]
     if not force and not _stale(LIB, srcs + HEADERS + [Path(__file__)]):
         return LIB
     LIB.parent.mkdir(exist_ok=True)
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG / "build" / tag if tag else PKG / "build"
+    objdir.mkdir(exist_ok=True, parents=True)
     objs = []
     procs = []
     for src in srcs:

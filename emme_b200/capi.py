@@ -7,7 +7,10 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libemme_b200.so"
+import os
+
+# EMME_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = Path(os.environ.get("EMME_B200_LIB", PKG / "lib" / "libemme_b200.so"))
 
 E_NO_DEVICE, E_CUDA, E_BAD_ORDER, E_STATE, E_INPUT = 1000, 1001, 1002, 1003, 1004
 

@@ -37,7 +37,10 @@ __constant__ GKTables c_gk31 = EMME_GK31_INIT;
 
 constexpr int STACK_SMEM = 8;    // right-sibling intervals kept in shared memory per lane
 constexpr int BLOCK = 128;
-constexpr int MIN_BLOCKS = 4;
+#ifndef EMME_ASM_MIN_BLOCKS
+#define EMME_ASM_MIN_BLOCKS 4
+#endif
+constexpr int MIN_BLOCKS = EMME_ASM_MIN_BLOCKS;
 
 // pair index p (diagonal-major: d = j-i ascending, i ascending) -> (i, j).
 // pairs with diagonal < d: T(d) = (d-1)*(2N-d)/2

@@ -123,39 +123,62 @@ struct EvalCounters {
 // Scaled modified Bessel ratios by Miller's algorithm (include/functions.h:381-408).
 // z = s/lambda, zc = 2/z = (2/s)*lambda.  Returns y0, y1, mu(+y0); the 4th element of the
 // reference's array (-z or z) is formed by the caller.
+// exact-order helpers with explicit fused multiply-adds (4 DFMA per complex multiply-add)
+EMME_HD cplx cfma(cplx a, cplx b, cplx c) {    // a*b + c
+    return mk(fma(a.re, b.re, fma(-a.im, b.im, c.re)), fma(a.re, b.im, fma(a.im, b.re, c.im)));
+}
+EMME_HD cplx cfms(cplx a, cplx b, cplx c) {    // c - a*b
+    return mk(fma(-a.re, b.re, fma(a.im, b.im, c.re)), fma(-a.re, b.im, fma(-a.im, b.re, c.im)));
+}
+// |p|^2 <= thr for non-negative doubles, on the integer pipe (NaN compares "greater": loop ends)
+EMME_HD bool le_nonneg(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(a) <= __double_as_longlong(b);
+#else
+    return a <= b;
+#endif
+}
+
 EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalCounters& cnt) {
     const double THRESHOLD = 2.e+7;
     const double az = sqrt(norm2(z));
-    // the order n is carried as a double (exact): no int->double conversion per trip
-    const double dn0 = floor(az) + 1.0;
-    double dn = dn0;
+    // the order n is carried as an int (loop control, integer pipe) and as a double (exact)
+    const int n0 = (int)(floor(az) + 1.0);
+    int n = n0;
+    double dn = (double)n0;
     // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared.
     const double thr2 = fmax(THRESHOLD * (dn * sqrt(norm2(zc))), THRESHOLD * THRESHOLD);
-    cplx p0 = mk(0., 0.), p1 = mk(1., 0.);
-    while (norm2(p1) <= thr2) {
-        const cplx c = dn * zc;
-        const cplx pt = p0 - c * p1;
-        p0 = p1;
-        p1 = pt;
+    // forward recurrence p_{k+1} = p_{k-1} - (2n/z) p_k, two trips per round (no register moves)
+    cplx pa = mk(0., 0.), pb = mk(1., 0.);   // pa = p_{k-1}, pb = p_k
+    for (;;) {
+        if (!le_nonneg(norm2(pb), thr2)) break;
+        pa = cfms(dn * zc, pb, pa);          // pa <- p_{k+1}
         dn += 1.0;
+        ++n;
+        if (!le_nonneg(norm2(pa), thr2)) { pb = pa; break; }
+        pb = cfms(dn * zc, pa, pb);          // pb <- p_{k+2}
+        dn += 1.0;
+        ++n;
     }
-    cnt.fwd += (unsigned)(dn - dn0);
-    y0 = recip(p1);
+    cnt.fwd += (unsigned)(n - n0);
+    y0 = recip(pb);
     y1 = mk(0., 0.);
     mu = mk(0., 0.);
+    --n;
     dn -= 1.0;
-    cnt.bwd += (unsigned)dn;
+    cnt.bwd += (unsigned)n;
     // 2*(Re z < 0 ? 1 - 2*(n & 1) : 1): alternates with n when Re z < 0
     const bool neg = z.re < 0;
+    double sg = (neg && (n & 1)) ? -2.0 : 2.0;
     const double flip = neg ? -1.0 : 1.0;
-    double sg = (neg && (((long long)dn) & 1)) ? -2.0 : 2.0;
-    for (; dn > 0.5; dn -= 1.0) {
-        const cplx c = dn * zc;
-        const cplx yt = c * y0 + y1;
+#pragma unroll 2
+    for (; n > 0; --n) {
+        const cplx yt = cfma(dn * zc, y0, y1);
         y1 = y0;
         y0 = yt;
-        mu = mu + sg * y1;
+        mu = mk(fma(sg, y1.re, mu.re), fma(sg, y1.im, mu.im));
         sg *= flip;
+        dn -= 1.0;
     }
     mu = mu + y0;
 }
