@@ -174,6 +174,7 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     s->grid_blocks = emme::assembly_grid_blocks(p->integration_start_points, device);
     // interval stack: at most integration_iteration_limit right siblings
     if (const char* e = std::getenv("EMME_REFILL_MIN")) s->refill_min = std::atoi(e);
+    if (const char* e = std::getenv("EMME_DENSE_GRID_PANEL")) emme::dense_force_grid_panel(std::atoi(e) != 0);
     if (s->refill_min < 1) s->refill_min = 1;
     if (s->refill_min > 32) s->refill_min = 32;
     s->spill_cap = p->integration_iteration_limit + 1 - emme::assembly_stack_smem();

@@ -181,6 +181,203 @@ panel_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, int* __restri
     }
 }
 
+// ------------------------------------------------------------------ panel, cluster variant
+// Same algorithm for panels of at most CLUSTER_MAX * TPB rows: the CTAs of ONE thread-block
+// cluster hold the panel (one thread per row, the NB row entries in REGISTERS -- the column
+// loop is unrolled at compile time through PanelSteps<>), candidates are published in the CTA's
+// own shared memory and read by the other CTAs through distributed shared memory, and the per-
+// column barrier is the hardware cluster barrier (~0.2 us) instead of a grid-wide software one.
+struct ClusterCand {
+    double val;
+    int pos;
+    int pad;
+    z_t row[NB];
+};
+
+template <int TPB>
+struct PanelState {
+    z_t a[NB];
+    int my_pos;
+    bool done;
+};
+
+template <int TPB, int C>
+__device__ __forceinline__ void panel_cluster_step(PanelState<TPB>& st, cg::cluster_group& cluster,
+                                                   ClusterCand (*s_cand)[1], ClusterCand* s_best,
+                                                   double* s_val, int* s_thr, int* s_misc, int k0,
+                                                   int jb, int* __restrict__ ipiv,
+                                                   int* __restrict__ info) {
+    if (C >= jb) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned crank = cluster.block_rank(), csz = cluster.num_blocks();
+    // ---- block-local candidate ----
+    double v = st.done ? -1.0 : fabs(st.a[C].x) + fabs(st.a[C].y);
+    int p = st.done ? 0x7fffffff : st.my_pos;
+    int t = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
+        const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
+        if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; t = t2; }
+    }
+    if (lane == 0) { s_val[warp] = v; s_thr[warp] = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bv = s_val[0];
+        int bt = s_thr[0];
+        for (int w = 1; w < TPB / 32; ++w)
+            if (s_val[w] > bv) { bv = s_val[w]; bt = s_thr[w]; }
+        s_misc[0] = bt;
+    }
+    __syncthreads();
+    ClusterCand* mine = &s_cand[C & 1][0];
+    if (threadIdx.x == s_misc[0]) {
+        mine->val = st.done ? -1.0 : fabs(st.a[C].x) + fabs(st.a[C].y);
+        mine->pos = st.my_pos;
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) mine->row[cc] = st.a[cc];
+    }
+    cluster.sync();
+    // ---- cluster-wide pivot: warp 0 reads every CTA's candidate through DSMEM ----
+    if (warp == 0) {
+        double bv = -2.0;
+        int bp = 0x7fffffff, bb = 0;
+        for (unsigned b = lane; b < csz; b += 32) {
+            const ClusterCand* cnd = cluster.map_shared_rank(mine, b);
+            const double cv = cnd->val;
+            const int cp = cnd->pos;
+            if (cv > bv || (cv == bv && cp < bp)) { bv = cv; bp = cp; bb = (int)b; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+            const int b2 = __shfl_xor_sync(0xffffffffu, bb, o);
+            if (v2 > bv || (v2 == bv && p2 < bp)) { bv = v2; bp = p2; bb = b2; }
+        }
+        // copy the winning row into local shared memory (one 16-byte element per lane)
+        const ClusterCand* best = cluster.map_shared_rank(mine, (unsigned)bb);
+        if (lane < NB) s_best->row[lane] = best->row[lane];
+        if (lane == 0) { s_best->val = bv; s_best->pos = bp; }
+    }
+    __syncthreads();
+    const double pv = s_best->val;
+    const int ppos = s_best->pos;
+    const int diag = k0 + C;
+    if (crank == 0 && threadIdx.x == 0) {
+        ipiv[diag] = ppos;
+        if (pv == 0.0 && *info == 0) *info = diag + 1;
+    }
+    const bool i_am_pivot = !st.done && st.my_pos == ppos;
+    if (!st.done && !i_am_pivot && st.my_pos == diag) st.my_pos = ppos;
+    if (i_am_pivot) { st.my_pos = diag; st.done = true; }
+    if (!st.done && pv > 0.0) {
+        const z_t l = zmul(st.a[C], zrecip(s_best->row[C]));
+        st.a[C] = l;
+#pragma unroll
+        for (int cc = C + 1; cc < NB; ++cc) zfms(st.a[cc], l, s_best->row[cc]);
+    }
+    __syncthreads();   // s_best / s_val are reused by the next column
+}
+
+template <int TPB, int C>
+struct PanelSteps {
+    static __device__ __forceinline__ void run(PanelState<TPB>& st, cg::cluster_group& cluster,
+                                               ClusterCand (*s_cand)[1], ClusterCand* s_best,
+                                               double* s_val, int* s_thr, int* s_misc, int k0, int jb,
+                                               int* ipiv, int* info) {
+        panel_cluster_step<TPB, C>(st, cluster, s_cand, s_best, s_val, s_thr, s_misc, k0, jb, ipiv, info);
+        PanelSteps<TPB, C + 1>::run(st, cluster, s_cand, s_best, s_val, s_thr, s_misc, k0, jb, ipiv, info);
+    }
+};
+template <int TPB>
+struct PanelSteps<TPB, NB> {
+    static __device__ __forceinline__ void run(PanelState<TPB>&, cg::cluster_group&, ClusterCand (*)[1],
+                                               ClusterCand*, double*, int*, int*, int, int, int*, int*) {}
+};
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
+panel_cluster_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, int* __restrict__ ipiv,
+                     int* __restrict__ info) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ ClusterCand s_cand[2][1];
+    __shared__ ClusterCand s_best;
+    __shared__ double s_val[TPB / 32];
+    __shared__ int s_thr[TPB / 32];
+    __shared__ int s_misc[2];
+    const int rows = dim - k0;
+    const int r = (int)cluster.block_rank() * TPB + threadIdx.x;
+    const bool have = r < rows;
+    PanelState<TPB> st;
+    st.my_pos = k0 + r;
+    st.done = !have;
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+        st.a[c] = (have && c < jb) ? W[(size_t)(k0 + r) * ld + k0 + c] : make_double2(0., 0.);
+    PanelSteps<TPB, 0>::run(st, cluster, s_cand, &s_best, s_val, s_thr, s_misc, k0, jb, ipiv, info);
+    cluster.sync();   // no CTA may exit while others still read its shared memory
+    if (have) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (c < jb) W[(size_t)st.my_pos * ld + k0 + c] = st.a[c];
+    }
+}
+
+constexpr int CL_TPB = 256;       // rows per CTA of the cluster panel kernel
+constexpr int CLUSTER_MAX = 16;   // non-portable cluster size (8 is the portable limit)
+
+// largest cluster size (power of two <= CLUSTER_MAX) the device can co-schedule for this kernel
+static int panel_cluster_limit() {
+    static int limit = -1;
+    if (limit >= 0) return limit;
+    limit = 0;
+    if (cudaFuncSetAttribute(panel_cluster_kernel<CL_TPB>,
+                             cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+    }
+    for (int csz = CLUSTER_MAX; csz >= 1; csz >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(csz);
+        cfg.blockDim = dim3(CL_TPB);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csz;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, panel_cluster_kernel<CL_TPB>, &cfg) == cudaSuccess && n >= 1) {
+            limit = csz;
+            break;
+        }
+        cudaGetLastError();
+    }
+    return limit;
+}
+
+static cudaError_t launch_panel_cluster(z_t* W, int ld, int dim, int k0, int jb, int* ipiv, int* info,
+                                        cudaStream_t stream) {
+    const int rows = dim - k0;
+    int csz = 1;
+    while (csz * CL_TPB < rows) csz <<= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csz);
+    cfg.blockDim = dim3(CL_TPB);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csz;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, panel_cluster_kernel<CL_TPB>, W, ld, dim, k0, jb, ipiv, info);
+}
+
 // ------------------------------------------------------------------ interchanges + block-row solve
 // One thread per column of [W(:, k0+jb:) | B(:, :)]: apply the jb row interchanges of the
 // panel, then forward-substitute with the unit-lower NB x NB block.
@@ -257,13 +454,14 @@ utrsm_kernel(const z_t* __restrict__ W, z_t* __restrict__ B, int ld, int k0, int
 // through shared memory.  FP64-pipe bound by construction (64 DFMA per 8 LDS.128).
 constexpr int GM = 64, GN = 64, GK = 16;
 
-__global__ void __launch_bounds__(256)
-zgemm_sub_kernel(z_t* __restrict__ C, int ldc, const z_t* __restrict__ A, int lda,
-                 const z_t* __restrict__ Bm, int ldb, int M, int N, int K) {
+__device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
+                                               const z_t* __restrict__ A, int lda,
+                                               const z_t* __restrict__ Bm, int ldb, int M, int N,
+                                               int K, int bx, int by) {
     __shared__ z_t sA[GK][GM + 1];
     __shared__ z_t sB[GK][GN];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    const int m0 = by * GM, n0 = bx * GN;
     z_t acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -323,6 +521,25 @@ zgemm_sub_kernel(z_t* __restrict__ C, int ldc, const z_t* __restrict__ A, int ld
             C[(size_t)m * ldc + n] = c;
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+zgemm_sub_kernel(z_t* __restrict__ C, int ldc, const z_t* __restrict__ A, int lda,
+                 const z_t* __restrict__ Bm, int ldb, int M, int N, int K) {
+    zgemm_sub_tile(C, ldc, A, lda, Bm, ldb, M, N, K, blockIdx.x, blockIdx.y);
+}
+
+// Trailing update of the augmented system in ONE launch: the same L21 (A) multiplies the
+// block row of W (C1 -= A*B1, N1 columns) and the block row of the right-hand sides
+// (C2 -= A*B2, N2 columns); column tiles [0, nx1) belong to the first product.
+__global__ void __launch_bounds__(256)
+zgemm_sub2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int N1, int nx1,
+                  z_t* __restrict__ C2, const z_t* __restrict__ B2, int N2, int ld,
+                  const z_t* __restrict__ A, int M, int K) {
+    if ((int)blockIdx.x < nx1)
+        zgemm_sub_tile(C1, ld, A, ld, B1, ld, M, N1, K, blockIdx.x, blockIdx.y);
+    else
+        zgemm_sub_tile(C2, ld, A, ld, B2, ld, M, N2, K, blockIdx.x - nx1, blockIdx.y);
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -409,6 +626,10 @@ cudaError_t measure_fp64_peak(double* tflops) {
     return cudaGetLastError();
 }
 
+// test hook: force the grid-cooperative panel kernel for every panel (EMME_DENSE_GRID_PANEL=1)
+static bool g_force_grid_panel = false;
+void dense_force_grid_panel(bool on) { g_force_grid_panel = on; }
+
 size_t dense_workspace_bytes(int dim) {
     const int nblk = (dim + PT - 1) / PT;
     return sizeof(PanelCand) * 2 * (size_t)nblk + sizeof(int) * (size_t)dim + 64;
@@ -431,25 +652,25 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
         int jb = dim - k0 < NB ? dim - k0 : NB;
         int rows = dim - k0;
         int nblk = (rows + PT - 1) / PT;
-        void* args[] = {&W, (void*)&ld, &dim, &k0, &jb, &ipiv, &xchg, &d_info};
-        e = cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(nblk), dim3(PT), args, 0, stream);
+        if (rows <= CL_TPB * panel_cluster_limit() && !g_force_grid_panel) {
+            e = launch_panel_cluster(W, ld, dim, k0, jb, ipiv, d_info, stream);
+        } else {
+            void* args[] = {&W, (void*)&ld, &dim, &k0, &jb, &ipiv, &xchg, &d_info};
+            e = cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(nblk), dim3(PT), args, 0, stream);
+        }
         if (e != cudaSuccess) return e;
         nl += 2;
         const int ncol = (dim - (k0 + jb)) + dim;
         swap_trsm_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(W, B, ld, dim, k0, jb, ipiv);
         const int M = dim - (k0 + jb);
         if (M > 0) {
-            nl += 2;
-            // trailing W
-            dim3 g1((M + GN - 1) / GN, (M + GM - 1) / GM);
-            zgemm_sub_kernel<<<g1, 256, 0, stream>>>(W + (size_t)(k0 + jb) * ld + (k0 + jb), ld,
-                                                     W + (size_t)(k0 + jb) * ld + k0, ld,
-                                                     W + (size_t)k0 * ld + (k0 + jb), ld, M, M, jb);
-            // right-hand sides
-            dim3 g2((dim + GN - 1) / GN, (M + GM - 1) / GM);
-            zgemm_sub_kernel<<<g2, 256, 0, stream>>>(B + (size_t)(k0 + jb) * ld, ld,
-                                                     W + (size_t)(k0 + jb) * ld + k0, ld,
-                                                     B + (size_t)k0 * ld, ld, M, dim, jb);
+            nl += 1;
+            const int nx1 = (M + GN - 1) / GN, nx2 = (dim + GN - 1) / GN;
+            dim3 g(nx1 + nx2, (M + GM - 1) / GM);
+            zgemm_sub2_kernel<<<g, 256, 0, stream>>>(
+                W + (size_t)(k0 + jb) * ld + (k0 + jb), W + (size_t)k0 * ld + (k0 + jb), M, nx1,
+                B + (size_t)(k0 + jb) * ld, B + (size_t)k0 * ld, dim, ld,
+                W + (size_t)(k0 + jb) * ld + k0, M, jb);
         }
     }
     // back substitution, lower triangle of X only

@@ -15,6 +15,7 @@ cudaError_t launch_trace_solve(void* W, void* B, int dim, void* workspace, void*
 // Ad = (A - Aold)/delta over n complex entries
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,
                           double di, int sms, cudaStream_t stream);
+void dense_force_grid_panel(bool on);
 // measured DFMA throughput (TFLOP/s) of the current device
 cudaError_t measure_fp64_peak(double* tflops);
 }  // namespace emme
