@@ -60,273 +60,204 @@ __device__ __forceinline__ z_t zdiv(z_t a, z_t b) {
 }
 
 // ------------------------------------------------------------------ panel factorisation
+// One thread per matrix row of the (dim-k0) x jb panel.  The thread keeps the NOT YET
+// ELIMINATED part of its row in registers as a window a[0..NB) whose first element is always
+// the current column: after every column the window shifts left by one, so the column loop is
+// a rolled loop with static register indices (an unrolled-by-column version was instruction-
+// fetch bound: 32 copies of the body, each executed once).  Multipliers and finished pivot rows
+// are stored to W at the row's ORIGINAL position as they are produced; the row interchanges are
+// implicit (each thread tracks its row's current position) and materialise in a final
+// read-all / barrier / write-all permutation.
+// Per column: block-local pivot candidate -> published together with its whole row window ->
+// ONE barrier -> every CTA picks the global winner and copies its row window into local shared
+// memory -> eliminate.  Two communication back ends:
+//   ClusterComm: the CTAs form one thread-block cluster; candidates live in shared memory and
+//                are read through DSMEM; barrier = hardware cluster barrier     (rows <= 4096)
+//   GridComm   : candidates in global memory, barrier = cooperative grid sync  (any size)
 constexpr int NB = DENSE_NB;      // panel width
-constexpr int PT = 128;           // threads (= rows) per CTA of the panel kernel
 
 struct PanelCand {                // what a CTA publishes per column step
     double val;                   // |re| + |im| of its best candidate (-1: none)
     int pos;                      // current row position of that candidate
     int pad;
-    z_t row[NB];                  // the candidate's panel row
+    z_t row[NB];                  // the candidate's row window (column c+k at index k)
 };
 
-__global__ void __launch_bounds__(PT)
-panel_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, int* __restrict__ ipiv,
-             PanelCand* __restrict__ xchg, int* __restrict__ info) {
-    cg::grid_group grid = cg::this_grid();
+struct ClusterComm {
+    cg::cluster_group cluster;
+    PanelCand* s_cand;            // [2] in this CTA's shared memory
+    __device__ __forceinline__ unsigned rank() const { return cluster.block_rank(); }
+    __device__ __forceinline__ unsigned size() const { return cluster.num_blocks(); }
+    __device__ __forceinline__ PanelCand* mine(int c) { return s_cand + (c & 1); }
+    __device__ __forceinline__ const PanelCand* peer(int c, unsigned b) {
+        return cluster.map_shared_rank(s_cand + (c & 1), b);
+    }
+    __device__ __forceinline__ void sync() { cluster.sync(); }
+    static __device__ __forceinline__ double ld(const double* p) { return *p; }
+    static __device__ __forceinline__ int ld(const int* p) { return *p; }
+};
+
+struct GridComm {
+    cg::grid_group grid;
+    PanelCand* xchg;              // [2][gridDim.x] in global memory
+    __device__ __forceinline__ unsigned rank() const { return blockIdx.x; }
+    __device__ __forceinline__ unsigned size() const { return gridDim.x; }
+    __device__ __forceinline__ PanelCand* mine(int c) { return xchg + (size_t)(c & 1) * gridDim.x + blockIdx.x; }
+    __device__ __forceinline__ const PanelCand* peer(int c, unsigned b) {
+        return xchg + (size_t)(c & 1) * gridDim.x + b;
+    }
+    __device__ __forceinline__ void sync() {
+        __threadfence();
+        grid.sync();
+    }
+    static __device__ __forceinline__ double ld(const double* p) { return __ldcg(p); }
+    static __device__ __forceinline__ int ld(const int* p) { return __ldcg(p); }
+};
+
+template <int TPB, class Comm>
+__device__ __forceinline__ void panel_body(Comm& comm, z_t* __restrict__ W, int ld, int dim, int k0,
+                                           int jb, int* __restrict__ ipiv, int* __restrict__ info) {
+    __shared__ PanelCand s_best;
+    __shared__ double s_val[TPB / 32];
+    __shared__ int s_thr[TPB / 32];
+    __shared__ int s_win;
     const int rows = dim - k0;
-    const int r = blockIdx.x * PT + threadIdx.x;
+    const int r = (int)comm.rank() * TPB + threadIdx.x;
     const bool have = r < rows;
-    const int nblk = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned csz = comm.size();
+    z_t* const myrow = W + (size_t)(k0 + r) * ld + k0;   // original position of this thread's row
     int my_pos = k0 + r;
     bool done = !have;
 
     z_t a[NB];
 #pragma unroll
-    for (int c = 0; c < NB; ++c)
-        a[c] = (have && c < jb) ? W[(size_t)(k0 + r) * ld + k0 + c] : make_double2(0., 0.);
+    for (int k = 0; k < NB; ++k) a[k] = (have && k < jb) ? myrow[k] : make_double2(0., 0.);
 
-    __shared__ double s_val[PT / 32];
-    __shared__ int s_thr[PT / 32];
-    __shared__ int s_best_blk;
-    __shared__ int s_winner;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        if (c < jb) {
-            // ---- block-local pivot candidate: max |re|+|im|, ties -> lowest position ----
-            double v = done ? -1.0 : fabs(a[c].x) + fabs(a[c].y);
-            int p = done ? 0x7fffffff : my_pos;
-            int t = threadIdx.x;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
-                const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
-                const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
-                if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; t = t2; }
-            }
-            if (lane == 0) { s_val[warp] = v; s_thr[warp] = t; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                // positions are unique, so comparing (val, thread->pos) needs the pos: recompute
-                double bv = s_val[0];
-                int bt = s_thr[0];
-                for (int w = 1; w < PT / 32; ++w)
-                    if (s_val[w] > bv) { bv = s_val[w]; bt = s_thr[w]; }
-                s_winner = bt;
-            }
-            __syncthreads();
-            PanelCand* mine = xchg + (size_t)(c & 1) * nblk + blockIdx.x;
-            if (threadIdx.x == s_winner) {
-                mine->val = done ? -1.0 : fabs(a[c].x) + fabs(a[c].y);
-                mine->pos = my_pos;
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) mine->row[cc] = a[cc];
-            }
-            __threadfence();
-            grid.sync();
-            // ---- global pivot: first warp scans the per-CTA candidates ----
-            if (warp == 0) {
-                double bv = -2.0;
-                int bp = 0x7fffffff, bb = 0;
-                for (int b = lane; b < nblk; b += 32) {
-                    const PanelCand* cnd = xchg + (size_t)(c & 1) * nblk + b;
-                    const double cv = __ldcg(&cnd->val);
-                    const int cp = __ldcg(&cnd->pos);
-                    if (cv > bv || (cv == bv && cp < bp)) { bv = cv; bp = cp; bb = b; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-                    const int b2 = __shfl_xor_sync(0xffffffffu, bb, o);
-                    if (v2 > bv || (v2 == bv && p2 < bp)) { bv = v2; bp = p2; bb = b2; }
-                }
-                if (lane == 0) s_best_blk = bb;
-            }
-            __syncthreads();
-            const PanelCand* best = xchg + (size_t)(c & 1) * nblk + s_best_blk;
-            const double pv = __ldcg(&best->val);
-            const int ppos = __ldcg(&best->pos);
-            const int diag = k0 + c;
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                ipiv[diag] = ppos;
-                if (pv == 0.0 && *info == 0) *info = diag + 1;  // exactly singular (LAPACK info > 0)
-            }
-            // ---- implicit interchange ----
-            const bool i_am_pivot = !done && my_pos == ppos;
-            if (!done && !i_am_pivot && my_pos == diag) my_pos = ppos;
-            if (i_am_pivot) { my_pos = diag; done = true; }
-            // ---- eliminate ----
-            if (!done && pv > 0.0) {
-                const z_t piv = make_double2(__ldcg(&best->row[c].x), __ldcg(&best->row[c].y));
-                const z_t l = zmul(a[c], zrecip(piv));
-                a[c] = l;
-#pragma unroll
-                for (int cc = c + 1; cc < NB; ++cc) {
-                    if (cc < jb) {
-                        const z_t u = make_double2(__ldcg(&best->row[cc].x), __ldcg(&best->row[cc].y));
-                        zfms(a[cc], l, u);
-                    }
-                }
-            }
-        }
-    }
-    if (have) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-            if (c < jb) W[(size_t)my_pos * ld + k0 + c] = a[c];
-    }
-}
-
-// ------------------------------------------------------------------ panel, cluster variant
-// Same algorithm for panels of at most CLUSTER_MAX * TPB rows: the CTAs of ONE thread-block
-// cluster hold the panel (one thread per row, the NB row entries in REGISTERS -- the column
-// loop is unrolled at compile time through PanelSteps<>), candidates are published in the CTA's
-// own shared memory and read by the other CTAs through distributed shared memory, and the per-
-// column barrier is the hardware cluster barrier (~0.2 us) instead of a grid-wide software one.
-struct ClusterCand {
-    double val;
-    int pos;
-    int pad;
-    z_t row[NB];
-};
-
-template <int TPB>
-struct PanelState {
-    z_t a[NB];
-    int my_pos;
-    bool done;
-};
-
-template <int TPB, int C>
-__device__ __forceinline__ void panel_cluster_step(PanelState<TPB>& st, cg::cluster_group& cluster,
-                                                   ClusterCand (*s_cand)[1], ClusterCand* s_best,
-                                                   double* s_val, int* s_thr, int* s_misc, int k0,
-                                                   int jb, int* __restrict__ ipiv,
-                                                   int* __restrict__ info) {
-    if (C >= jb) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned crank = cluster.block_rank(), csz = cluster.num_blocks();
-    // ---- block-local candidate ----
-    double v = st.done ? -1.0 : fabs(st.a[C].x) + fabs(st.a[C].y);
-    int p = st.done ? 0x7fffffff : st.my_pos;
-    int t = threadIdx.x;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
-        const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
-        const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
-        if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; t = t2; }
-    }
-    if (lane == 0) { s_val[warp] = v; s_thr[warp] = t; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double bv = s_val[0];
-        int bt = s_thr[0];
-        for (int w = 1; w < TPB / 32; ++w)
-            if (s_val[w] > bv) { bv = s_val[w]; bt = s_thr[w]; }
-        s_misc[0] = bt;
-    }
-    __syncthreads();
-    ClusterCand* mine = &s_cand[C & 1][0];
-    if (threadIdx.x == s_misc[0]) {
-        mine->val = st.done ? -1.0 : fabs(st.a[C].x) + fabs(st.a[C].y);
-        mine->pos = st.my_pos;
-#pragma unroll
-        for (int cc = 0; cc < NB; ++cc) mine->row[cc] = st.a[cc];
-    }
-    cluster.sync();
-    // ---- cluster-wide pivot: warp 0 reads every CTA's candidate through DSMEM ----
-    if (warp == 0) {
-        double bv = -2.0;
-        int bp = 0x7fffffff, bb = 0;
-        for (unsigned b = lane; b < csz; b += 32) {
-            const ClusterCand* cnd = cluster.map_shared_rank(mine, b);
-            const double cv = cnd->val;
-            const int cp = cnd->pos;
-            if (cv > bv || (cv == bv && cp < bp)) { bv = cv; bp = cp; bb = (int)b; }
-        }
+#pragma unroll 1
+    for (int c = 0; c < jb; ++c) {
+        // ---- block-local pivot candidate: max |re|+|im|, ties -> lowest position ----
+        const double myv = done ? -1.0 : fabs(a[0].x) + fabs(a[0].y);
+        double v = myv;
+        int p = done ? 0x7fffffff : my_pos;
+        int t = threadIdx.x;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-            const int b2 = __shfl_xor_sync(0xffffffffu, bb, o);
-            if (v2 > bv || (v2 == bv && p2 < bp)) { bv = v2; bp = p2; bb = b2; }
+            const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
+            const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
+            if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; t = t2; }
         }
-        // copy the winning row into local shared memory (one 16-byte element per lane)
-        const ClusterCand* best = cluster.map_shared_rank(mine, (unsigned)bb);
-        if (lane < NB) s_best->row[lane] = best->row[lane];
-        if (lane == 0) { s_best->val = bv; s_best->pos = bp; }
-    }
-    __syncthreads();
-    const double pv = s_best->val;
-    const int ppos = s_best->pos;
-    const int diag = k0 + C;
-    if (crank == 0 && threadIdx.x == 0) {
-        ipiv[diag] = ppos;
-        if (pv == 0.0 && *info == 0) *info = diag + 1;
-    }
-    const bool i_am_pivot = !st.done && st.my_pos == ppos;
-    if (!st.done && !i_am_pivot && st.my_pos == diag) st.my_pos = ppos;
-    if (i_am_pivot) { st.my_pos = diag; st.done = true; }
-    if (!st.done && pv > 0.0) {
-        const z_t l = zmul(st.a[C], zrecip(s_best->row[C]));
-        st.a[C] = l;
+        if (lane == 0) { s_val[warp] = v; s_thr[warp] = t; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double bv = s_val[0];
+            int bt = s_thr[0];
+            for (int w = 1; w < TPB / 32; ++w)
+                if (s_val[w] > bv) { bv = s_val[w]; bt = s_thr[w]; }
+            s_win = bt;
+        }
+        __syncthreads();
+        if (threadIdx.x == s_win) {
+            PanelCand* mine = comm.mine(c);
+            mine->val = myv;
+            mine->pos = my_pos;
 #pragma unroll
-        for (int cc = C + 1; cc < NB; ++cc) zfms(st.a[cc], l, s_best->row[cc]);
+            for (int k = 0; k < NB; ++k) mine->row[k] = a[k];
+        }
+        comm.sync();
+        // ---- global pivot: warp 0 scans the per-CTA candidates, copies the winner's window ----
+        if (warp == 0) {
+            double bv = -2.0;
+            int bp = 0x7fffffff, bb = 0;
+            for (unsigned b = lane; b < csz; b += 32) {
+                const PanelCand* cnd = comm.peer(c, b);
+                const double cv = Comm::ld(&cnd->val);
+                const int cp = Comm::ld(&cnd->pos);
+                if (cv > bv || (cv == bv && cp < bp)) { bv = cv; bp = cp; bb = (int)b; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int b2 = __shfl_xor_sync(0xffffffffu, bb, o);
+                if (v2 > bv || (v2 == bv && p2 < bp)) { bv = v2; bp = p2; bb = b2; }
+            }
+            const PanelCand* best = comm.peer(c, (unsigned)bb);
+            if (lane < NB)
+                s_best.row[lane] = make_double2(Comm::ld(&best->row[lane].x), Comm::ld(&best->row[lane].y));
+            if (lane == 0) { s_best.val = bv; s_best.pos = bp; }
+        }
+        __syncthreads();
+        const double pv = s_best.val;
+        const int ppos = s_best.pos;
+        const int diag = k0 + c;
+        if (comm.rank() == 0 && threadIdx.x == 0) {
+            ipiv[diag] = ppos;
+            if (pv == 0.0 && *info == 0) *info = diag + 1;   // exactly singular (LAPACK info > 0)
+        }
+        // ---- implicit interchange ----
+        const bool i_am_pivot = !done && my_pos == ppos;
+        if (!done && !i_am_pivot && my_pos == diag) my_pos = ppos;
+        if (i_am_pivot) {
+            // this row is U's row `diag`: its window is final, store it at the original position
+            my_pos = diag;
+            done = true;
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (c + k < jb) myrow[c + k] = a[k];
+        }
+        // ---- eliminate, then shift the window ----
+        if (!done) {
+            if (pv > 0.0) {
+                const z_t l = zmul(a[0], zrecip(s_best.row[0]));
+                myrow[c] = l;
+#pragma unroll
+                for (int k = 1; k < NB; ++k) zfms(a[k], l, s_best.row[k]);
+            } else {
+                myrow[c] = a[0];
+            }
+#pragma unroll
+            for (int k = 0; k < NB - 1; ++k) a[k] = a[k + 1];
+            a[NB - 1] = make_double2(0., 0.);
+        }
+        __syncthreads();   // s_best / s_val / s_win are reused by the next column
     }
-    __syncthreads();   // s_best / s_val are reused by the next column
+    // ---- materialise the interchanges: read every moved row, barrier, write it to its place ----
+    const bool moved = have && my_pos != k0 + r;
+    if (moved) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) a[k] = k < jb ? myrow[k] : make_double2(0., 0.);
+    }
+    comm.sync();
+    if (moved) {
+        z_t* dst = W + (size_t)my_pos * ld + k0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+            if (k < jb) dst[k] = a[k];
+    }
 }
 
-template <int TPB, int C>
-struct PanelSteps {
-    static __device__ __forceinline__ void run(PanelState<TPB>& st, cg::cluster_group& cluster,
-                                               ClusterCand (*s_cand)[1], ClusterCand* s_best,
-                                               double* s_val, int* s_thr, int* s_misc, int k0, int jb,
-                                               int* ipiv, int* info) {
-        panel_cluster_step<TPB, C>(st, cluster, s_cand, s_best, s_val, s_thr, s_misc, k0, jb, ipiv, info);
-        PanelSteps<TPB, C + 1>::run(st, cluster, s_cand, s_best, s_val, s_thr, s_misc, k0, jb, ipiv, info);
-    }
-};
-template <int TPB>
-struct PanelSteps<TPB, NB> {
-    static __device__ __forceinline__ void run(PanelState<TPB>&, cg::cluster_group&, ClusterCand (*)[1],
-                                               ClusterCand*, double*, int*, int*, int, int, int*, int*) {}
-};
+constexpr int PT = 128;           // rows per CTA, grid-cooperative variant
+constexpr int CL_TPB = 256;       // rows per CTA, cluster variant
+constexpr int CLUSTER_MAX = 16;   // non-portable cluster size (8 is the portable limit)
+
+__global__ void __launch_bounds__(PT)
+panel_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, int* __restrict__ ipiv,
+             PanelCand* __restrict__ xchg, int* __restrict__ info) {
+    GridComm comm{cg::this_grid(), xchg};
+    panel_body<PT>(comm, W, ld, dim, k0, jb, ipiv, info);
+}
 
 template <int TPB>
 __global__ void __launch_bounds__(TPB)
 panel_cluster_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, int* __restrict__ ipiv,
                      int* __restrict__ info) {
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ ClusterCand s_cand[2][1];
-    __shared__ ClusterCand s_best;
-    __shared__ double s_val[TPB / 32];
-    __shared__ int s_thr[TPB / 32];
-    __shared__ int s_misc[2];
-    const int rows = dim - k0;
-    const int r = (int)cluster.block_rank() * TPB + threadIdx.x;
-    const bool have = r < rows;
-    PanelState<TPB> st;
-    st.my_pos = k0 + r;
-    st.done = !have;
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-        st.a[c] = (have && c < jb) ? W[(size_t)(k0 + r) * ld + k0 + c] : make_double2(0., 0.);
-    PanelSteps<TPB, 0>::run(st, cluster, s_cand, &s_best, s_val, s_thr, s_misc, k0, jb, ipiv, info);
-    cluster.sync();   // no CTA may exit while others still read its shared memory
-    if (have) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-            if (c < jb) W[(size_t)st.my_pos * ld + k0 + c] = st.a[c];
-    }
+    __shared__ PanelCand s_cand[2];
+    ClusterComm comm{cg::this_cluster(), s_cand};
+    panel_body<TPB>(comm, W, ld, dim, k0, jb, ipiv, info);
+    comm.sync();   // no CTA may exit while others can still read its shared memory
 }
-
-constexpr int CL_TPB = 256;       // rows per CTA of the cluster panel kernel
-constexpr int CLUSTER_MAX = 16;   // non-portable cluster size (8 is the portable limit)
 
 // largest cluster size (power of two <= CLUSTER_MAX) the device can co-schedule for this kernel
 static int panel_cluster_limit() {
