@@ -58,6 +58,9 @@ struct emme_solver {
     emme_stats stats{};
     unsigned long long launches = 0;
     int refill_min = 16;
+    int optimistic = 1;               // try the interchange-free factorisation first
+    unsigned long long pivot_fallbacks = 0;
+    int* d_flag = nullptr;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
 };
 
@@ -131,6 +134,7 @@ int emme_destroy(emme_solver* s) {
     cudaFree(s->d_dense_ws);
     cudaFree(s->d_trace);
     cudaFree(s->d_info);
+    cudaFree(s->d_flag);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -175,6 +179,7 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     // interval stack: at most integration_iteration_limit right siblings
     if (const char* e = std::getenv("EMME_REFILL_MIN")) s->refill_min = std::atoi(e);
     if (const char* e = std::getenv("EMME_DENSE_GRID_PANEL")) emme::dense_force_grid_panel(std::atoi(e) != 0);
+    if (const char* e = std::getenv("EMME_DENSE_NBO")) emme::dense_set_outer_block(std::atoi(e));
     if (s->refill_min < 1) s->refill_min = 1;
     if (s->refill_min > 32) s->refill_min = 32;
     s->spill_cap = p->integration_iteration_limit + 1 - emme::assembly_stack_smem();
@@ -186,6 +191,9 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     }
     CU(cudaMalloc(&s->d_trace, sizeof(double2)));
     CU(cudaMalloc(&s->d_info, sizeof(int)));
+    CU(cudaMalloc(&s->d_flag, sizeof(int)));
+    if (const char* e = std::getenv("EMME_DENSE_OPTIMISTIC")) s->optimistic = std::atoi(e) != 0;
+    if (const char* e = std::getenv("EMME_DENSE_TAU")) emme::dense_set_pivot_threshold(std::atof(e));
     *out = s.release();
     return 0;
 }
@@ -247,21 +255,38 @@ int emme_assemble(emme_solver* s, double wr, double wi, void* host_out) {
     return collect_stats(s);
 }
 
+}  // extern "C" (templates below)
+
 // ---- dense step on (A, Ad): delta = -1/trace(A^-1 Ad); A is preserved, Ad destroyed ----
-static int dense_delta(emme_solver* s, zc* delta) {
+// First the optimistic factorisation (no interchanges, verified against the partial-pivoting
+// criterion on the fly); if the verification fails, `restore_rhs` rebuilds Ad and the step is
+// repeated with the pivoting kernels.
+template <class RestoreRhs>
+static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, s->stream));
-    CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
-    CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
-                                s->stream, &s->launches));
-    CU(cudaEventRecord(e1, s->stream));
     double tr[2];
-    int info = 0;
-    CU(cudaMemcpyAsync(tr, s->d_trace, sizeof tr, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    int info = 0, flag = 0;
+    for (int attempt = s->optimistic ? 0 : 1; attempt < 2; ++attempt) {
+        const int optimistic = attempt == 0;
+        if (attempt == 1 && s->optimistic) {
+            int rc = restore_rhs();
+            if (rc) return rc;
+            ++s->pivot_fallbacks;
+        }
+        CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
+        CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
+                                    s->stream, &s->launches, optimistic, s->d_flag));
+        CU(cudaEventRecord(e1, s->stream));
+        CU(cudaMemcpyAsync(tr, s->d_trace, sizeof tr, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));
+        if (optimistic)
+            CU(cudaMemcpyAsync(&flag, s->d_flag, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (!optimistic || flag == 0) break;
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
@@ -278,6 +303,8 @@ static int dense_delta(emme_solver* s, zc* delta) {
     }
     return 0;
 }
+
+extern "C" {
 
 static int secant(emme_solver* s) {
     CU(emme::launch_secant(s->A, s->Aold, s->Ad, (size_t)s->dim * s->dim, s->dw.real(),
@@ -347,7 +374,14 @@ int emme_step_begin(emme_solver* s) {
     if (!s->seeded) return fail(EMME_E_STATE, "emme_newton_trace_step before emme_seed");
     CU(cudaSetDevice(s->device));
     zc delta;
-    int rc = dense_delta(s, &delta);  // include/solver.h:130-139
+    const zc dw_prev = s->dw;
+    int rc = dense_delta(s, &delta, [&]() -> int {   // include/solver.h:130-139
+        // A' = (A - A_old)/delta_prev is rebuilt from the intact A and A_old
+        CU(emme::launch_secant(s->A, s->Aold, s->Ad, (size_t)s->dim * s->dim, dw_prev.real(),
+                               dw_prev.imag(), s->sms, s->stream));
+        ++s->launches;
+        return 0;
+    });
     s->dw = delta;
     s->w += delta;  // :140 (the reference updates omega before it checks info)
     if (rc) return rc;
@@ -394,7 +428,10 @@ int emme_trace_delta(emme_solver* s, const void* host_A, const void* host_Ad, do
     CU(cudaMemcpyAsync(s->A, host_A, s->bytes(), cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->Ad, host_Ad, s->bytes(), cudaMemcpyHostToDevice, s->stream));
     zc delta;
-    rc = dense_delta(s, &delta);
+    rc = dense_delta(s, &delta, [&]() -> int {
+        CU(cudaMemcpyAsync(s->Ad, host_Ad, s->bytes(), cudaMemcpyHostToDevice, s->stream));
+        return 0;
+    });
     if (dr) *dr = delta.real();
     if (di) *di = delta.imag();
     return rc;
@@ -422,6 +459,7 @@ int emme_get_stats(const emme_solver* s, emme_stats* out) {
     if (!out) return fail(-2, "null output");
     *out = s->stats;
     out->launches = s->launches;
+    out->pivot_fallbacks = s->pivot_fallbacks;
     return 0;
 }
 

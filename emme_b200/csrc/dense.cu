@@ -238,6 +238,82 @@ __device__ __forceinline__ void panel_body(Comm& comm, z_t* __restrict__ W, int 
     }
 }
 
+// ------------------------------------------------------------------ panel, optimistic variant
+// Partial pivoting keeps the diagonal whenever |a_cc| >= |a_ic| for all i > c (LAPACK's izamax
+// criterion |re|+|im|, ties to the lowest row).  EMME's matrices are diagonally strong (diagonal
+// 1+1/tau resp. 2*tau/beta_e*b_i against O(dx) quadrature entries), so on them partial pivoting
+// never interchanges rows.  This kernel factors a panel WITHOUT interchanges -- which removes the
+// per-column pivot search and with it every inter-CTA dependency -- and records, for every
+// multiplier it forms, whether partial pivoting would have accepted the diagonal
+// (|a_ic| <= tau*|a_cc| with tau = 1 by default).  If the flag stays clear the factorisation IS
+// the partial-pivoting one; if it is raised the host discards the result and repeats the dense
+// step with the pivoting kernels above.  Every CTA first factors the jb x jb diagonal block
+// redundantly in shared memory (one warp), then each thread eliminates its own row against it.
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
+panel_nopiv_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, double tau,
+                   int* __restrict__ flag, int* __restrict__ info) {
+    __shared__ z_t sD[NB][NB + 1];     // diagonal block: strict lower = L11, upper = U11
+    __shared__ z_t sInv[NB];           // 1/u_cc
+    __shared__ double sAbs[NB];        // |u_cc| (cabs1)
+    for (int e = threadIdx.x; e < NB * NB; e += TPB) {
+        const int rr = e / NB, cc = e % NB;
+        sD[rr][cc] = (rr < jb && cc < jb) ? W[(size_t)(k0 + rr) * ld + k0 + cc] : make_double2(0., 0.);
+    }
+    __syncthreads();
+    int bad = 0;
+    if (threadIdx.x < 32) {
+        const int i = threadIdx.x;     // lane = row of the diagonal block
+        for (int c = 0; c < jb; ++c) {
+            const z_t u = sD[c][c];
+            const double ua = fabs(u.x) + fabs(u.y);
+            const z_t inv = ua > 0.0 ? zrecip(u) : make_double2(0., 0.);
+            if (i == 0) {
+                sInv[c] = inv;
+                sAbs[c] = ua;
+                if (ua == 0.0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + c + 1);
+            }
+            if (i > c && i < jb) {
+                const z_t num = sD[i][c];
+                if (fabs(num.x) + fabs(num.y) > tau * ua) bad = 1;
+                const z_t l = zmul(num, inv);
+                sD[i][c] = l;
+                for (int k = c + 1; k < jb; ++k) zfms(sD[i][k], l, sD[c][k]);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int r = blockIdx.x * TPB + threadIdx.x;      // row offset below k0
+    if (r < dim - k0) {
+        z_t* myrow = W + (size_t)(k0 + r) * ld + k0;
+        if (r < jb) {
+            // rows of the diagonal block: CTA 0 writes the factored block back
+            if (blockIdx.x == 0) {
+                for (int c = 0; c < jb; ++c) myrow[c] = sD[r][c];
+            }
+        } else {
+            z_t a[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) a[k] = k < jb ? myrow[k] : make_double2(0., 0.);
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < jb) {
+                    if (fabs(a[c].x) + fabs(a[c].y) > tau * sAbs[c]) bad = 1;
+                    const z_t l = zmul(a[c], sInv[c]);
+                    a[c] = l;
+#pragma unroll
+                    for (int k = c + 1; k < NB; ++k) zfms(a[k], l, sD[c][k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (k < jb) myrow[k] = a[k];
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 constexpr int PT = 128;           // rows per CTA, grid-cooperative variant
 constexpr int CL_TPB = 256;       // rows per CTA, cluster variant
 constexpr int CLUSTER_MAX = 16;   // non-portable cluster size (8 is the portable limit)
@@ -310,11 +386,34 @@ static cudaError_t launch_panel_cluster(z_t* W, int ld, int dim, int k0, int jb,
 }
 
 // ------------------------------------------------------------------ interchanges + block-row solve
-// One thread per column of [W(:, k0+jb:) | B(:, :)]: apply the jb row interchanges of the
-// panel, then forward-substitute with the unit-lower NB x NB block.
+// Column sets are given as two ranges: columns [0,n1) start at p1, columns [n1,n1+n2) at p2
+// (both with leading dimension ld); one thread per column, coalesced across threads.
+__device__ __forceinline__ z_t* column_ptr(z_t* p1, int n1, z_t* p2, int col) {
+    return col < n1 ? p1 + col : p2 + (col - n1);
+}
+
+// Apply row interchanges kb .. kb+count-1 (row k <-> ipiv[k]), in order.
 __global__ void __launch_bounds__(128)
-swap_trsm_kernel(z_t* __restrict__ W, z_t* __restrict__ B, int ld, int dim, int k0, int jb,
-                 const int* __restrict__ ipiv) {
+laswp_kernel(z_t* __restrict__ p1, int n1, z_t* __restrict__ p2, int n2, int ld, int kb, int count,
+             const int* __restrict__ ipiv) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n1 + n2) return;
+    z_t* M = column_ptr(p1, n1, p2, col);
+    for (int c = 0; c < count; ++c) {
+        const int p = ipiv[kb + c];
+        if (p != kb + c) {
+            const z_t t1 = M[(size_t)(kb + c) * ld], t2 = M[(size_t)p * ld];
+            M[(size_t)(kb + c) * ld] = t2;
+            M[(size_t)p * ld] = t1;
+        }
+    }
+}
+
+// Optionally apply the interchanges of panel (k0, jb), then forward-substitute rows
+// k0 .. k0+jb-1 with the unit-lower jb x jb block L11 = W[k0:k0+jb, k0:k0+jb].
+__global__ void __launch_bounds__(128)
+swap_trsm_kernel(const z_t* __restrict__ W, z_t* __restrict__ p1, int n1, z_t* __restrict__ p2, int n2,
+                 int ld, int k0, int jb, const int* __restrict__ ipiv, int do_swap) {
     __shared__ z_t sL[NB][NB + 1];
     __shared__ int sP[NB];
     for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
@@ -323,20 +422,19 @@ swap_trsm_kernel(z_t* __restrict__ W, z_t* __restrict__ B, int ld, int dim, int 
     }
     if (threadIdx.x < NB) sP[threadIdx.x] = threadIdx.x < jb ? ipiv[k0 + threadIdx.x] : 0;
     __syncthreads();
-    const int nW = dim - (k0 + jb);                 // columns of W right of the panel
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= nW + dim) return;
-    z_t* M = col < nW ? W + (k0 + jb + col) : B + (col - nW);
-    // interchanges, in order
-    for (int c = 0; c < jb; ++c) {
-        const int p = sP[c];
-        if (p != k0 + c) {
-            const z_t t1 = M[(size_t)(k0 + c) * ld], t2 = M[(size_t)p * ld];
-            M[(size_t)(k0 + c) * ld] = t2;
-            M[(size_t)p * ld] = t1;
+    if (col >= n1 + n2) return;
+    z_t* M = column_ptr(p1, n1, p2, col);
+    if (do_swap) {
+        for (int c = 0; c < jb; ++c) {
+            const int p = sP[c];
+            if (p != k0 + c) {
+                const z_t t1 = M[(size_t)(k0 + c) * ld], t2 = M[(size_t)p * ld];
+                M[(size_t)(k0 + c) * ld] = t2;
+                M[(size_t)p * ld] = t1;
+            }
         }
     }
-    // unit-lower solve on rows k0 .. k0+jb-1
     z_t x[NB];
 #pragma unroll
     for (int rr = 0; rr < NB; ++rr) x[rr] = rr < jb ? M[(size_t)(k0 + rr) * ld] : make_double2(0., 0.);
@@ -383,49 +481,61 @@ utrsm_kernel(const z_t* __restrict__ W, z_t* __restrict__ B, int ld, int k0, int
 // C[M x N] -= A[M x K] * Bm[K x N], all row-major with their own leading dimensions.
 // 64x64 tile per CTA, 256 threads, 4x4 complex accumulators per thread, K slabs of 16 staged
 // through shared memory.  FP64-pipe bound by construction (64 DFMA per 8 LDS.128).
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 64, GN = 64, GK = 8;
 
+// Software-pipelined: while the DFMAs of k-slab s run out of shared memory, the global loads of
+// slab s+1 are in flight into registers; one __syncthreads per slab (double-buffered smem).
 __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
                                                const z_t* __restrict__ A, int lda,
                                                const z_t* __restrict__ Bm, int ldb, int M, int N,
                                                int K, int bx, int by) {
-    __shared__ z_t sA[GK][GM + 1];
-    __shared__ z_t sB[GK][GN];
+    __shared__ z_t sA[2][GK][GM + 1];
+    __shared__ z_t sB[2][GK][GN];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = by * GM, n0 = bx * GN;
+    // element ownership for the global->shared staging (2 of A, 2 of B per thread)
+    const int am = threadIdx.x >> 3, ak = threadIdx.x & 7;          // A: rows am, am+32; col ak
+    const int bk = threadIdx.x >> 6, bn = threadIdx.x & 63;         // B: rows bk, bk+4;  col bn
+    const bool a_ok0 = m0 + am < M, a_ok1 = m0 + am + 32 < M, b_ok = n0 + bn < N;
+    const z_t* Ap0 = A + (size_t)(m0 + am) * lda + ak;
+    const z_t* Ap1 = A + (size_t)(m0 + am + 32) * lda + ak;
+    const z_t* Bp0 = Bm + (size_t)bk * ldb + n0 + bn;
+    const z_t* Bp1 = Bm + (size_t)(bk + 4) * ldb + n0 + bn;
+    const z_t zero = make_double2(0., 0.);
+
     z_t acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = make_double2(0., 0.);
+        for (int j = 0; j < 4; ++j) acc[i][j] = zero;
 
+    z_t ra0, ra1, rb0, rb1;
+    auto fetch = [&](int kk) {
+        ra0 = (a_ok0 && kk + ak < K) ? Ap0[kk] : zero;
+        ra1 = (a_ok1 && kk + ak < K) ? Ap1[kk] : zero;
+        rb0 = (b_ok && kk + bk < K) ? Bp0[(size_t)kk * ldb] : zero;
+        rb1 = (b_ok && kk + bk + 4 < K) ? Bp1[(size_t)kk * ldb] : zero;
+    };
+    auto stage = [&](int buf) {
+        sA[buf][ak][am] = ra0;
+        sA[buf][ak][am + 32] = ra1;
+        sB[buf][bk][bn] = rb0;
+        sB[buf][bk + 4][bn] = rb1;
+    };
+    fetch(0);
+    stage(0);
+    __syncthreads();
+    int buf = 0;
     for (int kk = 0; kk < K; kk += GK) {
-        // A tile: GM rows x GK cols -> sA[k][m]; 1024 elements / 256 threads
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = threadIdx.x + e * 256;
-            const int m = idx / GK, k = idx % GK;
-            z_t v = make_double2(0., 0.);
-            if (m0 + m < M && kk + k < K) v = A[(size_t)(m0 + m) * lda + kk + k];
-            sA[k][m] = v;
-        }
-        // B tile: GK rows x GN cols -> sB[k][n]
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = threadIdx.x + e * 256;
-            const int k = idx / GN, n = idx % GN;
-            z_t v = make_double2(0., 0.);
-            if (kk + k < K && n0 + n < N) v = Bm[(size_t)(kk + k) * ldb + n0 + n];
-            sB[k][n] = v;
-        }
-        __syncthreads();
+        const bool more = kk + GK < K;
+        if (more) fetch(kk + GK);
 #pragma unroll
         for (int k = 0; k < GK; ++k) {
             z_t av[4], bv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = sA[k][ty * 4 + i];
+            for (int i = 0; i < 4; ++i) av[i] = sA[buf][k][ty * 4 + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = sB[k][tx + 16 * j];
+            for (int j = 0; j < 4; ++j) bv[j] = sB[buf][k][tx + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -436,7 +546,11 @@ __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
                     acc[i][j].y = fma(av[i].y, bv[j].x, acc[i][j].y);
                 }
         }
-        __syncthreads();
+        if (more) {
+            stage(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -454,7 +568,7 @@ __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 zgemm_sub_kernel(z_t* __restrict__ C, int ldc, const z_t* __restrict__ A, int lda,
                  const z_t* __restrict__ Bm, int ldb, int M, int N, int K) {
     zgemm_sub_tile(C, ldc, A, lda, Bm, ldb, M, N, K, blockIdx.x, blockIdx.y);
@@ -463,7 +577,7 @@ zgemm_sub_kernel(z_t* __restrict__ C, int ldc, const z_t* __restrict__ A, int ld
 // Trailing update of the augmented system in ONE launch: the same L21 (A) multiplies the
 // block row of W (C1 -= A*B1, N1 columns) and the block row of the right-hand sides
 // (C2 -= A*B2, N2 columns); column tiles [0, nx1) belong to the first product.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 zgemm_sub2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int N1, int nx1,
                   z_t* __restrict__ C2, const z_t* __restrict__ B2, int N2, int ld,
                   const z_t* __restrict__ A, int M, int K) {
@@ -566,9 +680,22 @@ size_t dense_workspace_bytes(int dim) {
     return sizeof(PanelCand) * 2 * (size_t)nblk + sizeof(int) * (size_t)dim + 64;
 }
 
+static int g_nbo = 0;     // outer block width (multiple of NB); 0 = choose by size
+void dense_set_outer_block(int nbo) {
+    g_nbo = nbo <= 0 ? 0 : (nbo < NB ? NB : (nbo / NB) * NB);
+}
+static double g_tau = 4.0;   // optimistic path accepts the diagonal while |a_ic| <= tau*|a_cc|
+void dense_set_pivot_threshold(double tau) { g_tau = tau; }
+
 // W (dim x dim, destroyed) and B (dim x dim, destroyed): trace(W^-1 B) -> *d_trace (device).
+//
+// Two-level right-looking LU: outer blocks of g_nbo columns are factored by NB-wide panels whose
+// updates stay inside the outer block; the rest of the matrix and the right-hand sides see one
+// interchange pass, a block-row solve and ONE rank-g_nbo GEMM per outer block (K = 128 keeps the
+// FP64 pipe busy; K = 32 was dominated by the C-tile read-modify-write).
 cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, void* d_trace,
-                               int* d_info, cudaStream_t stream, unsigned long long* n_launches) {
+                               int* d_info, cudaStream_t stream, unsigned long long* n_launches,
+                               int optimistic, int* d_flag) {
     unsigned long long nl = 0;
     z_t* W = (z_t*)Wv;
     z_t* B = (z_t*)Bv;
@@ -578,45 +705,99 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
     int* ipiv = (int*)((char*)workspace + sizeof(PanelCand) * 2 * (size_t)nblk_max);
     cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-
-    for (int k0 = 0; k0 < dim; k0 += NB) {
-        int jb = dim - k0 < NB ? dim - k0 : NB;
-        int rows = dim - k0;
-        int nblk = (rows + PT - 1) / PT;
-        if (rows <= CL_TPB * panel_cluster_limit() && !g_force_grid_panel) {
-            e = launch_panel_cluster(W, ld, dim, k0, jb, ipiv, d_info, stream);
-        } else {
-            void* args[] = {&W, (void*)&ld, &dim, &k0, &jb, &ipiv, &xchg, &d_info};
-            e = cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(nblk), dim3(PT), args, 0, stream);
-        }
+    // small systems are latency bound: single-level blocking means fewer launches
+    const int NBO = g_nbo > 0 ? g_nbo : (dim <= 2048 ? NB : 128);
+    if (optimistic) {
+        e = cudaMemsetAsync(d_flag, 0, sizeof(int), stream);
         if (e != cudaSuccess) return e;
-        nl += 2;
-        const int ncol = (dim - (k0 + jb)) + dim;
-        swap_trsm_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(W, B, ld, dim, k0, jb, ipiv);
-        const int M = dim - (k0 + jb);
-        if (M > 0) {
-            nl += 1;
-            const int nx1 = (M + GN - 1) / GN, nx2 = (dim + GN - 1) / GN;
-            dim3 g(nx1 + nx2, (M + GM - 1) / GM);
-            zgemm_sub2_kernel<<<g, 256, 0, stream>>>(
-                W + (size_t)(k0 + jb) * ld + (k0 + jb), W + (size_t)k0 * ld + (k0 + jb), M, nx1,
-                B + (size_t)(k0 + jb) * ld, B + (size_t)k0 * ld, dim, ld,
-                W + (size_t)(k0 + jb) * ld + k0, M, jb);
-        }
     }
-    // back substitution, lower triangle of X only
-    const int last = ((dim - 1) / NB) * NB;
-    for (int k0 = last; k0 >= 0; k0 -= NB) {
-        const int jb = dim - k0 < NB ? dim - k0 : NB;
-        const int ncols = k0 + jb;   // columns c <= last row of this block
-        utrsm_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(W, B, ld, k0, jb, ncols);
-        nl += 1;
-        if (k0 > 0) {
-            nl += 1;
-            dim3 g((k0 + GN - 1) / GN, (k0 + GM - 1) / GM);
-            zgemm_sub_kernel<<<g, 256, 0, stream>>>(B, ld, W + k0, ld, B + (size_t)k0 * ld, ld, k0,
-                                                    k0, jb);
+    auto at = [&](z_t* M, int r, int c) { return M + (size_t)r * ld + c; };
+    auto gemm1 = [&](z_t* C, const z_t* A, const z_t* Bm, int M, int N, int K) {
+        if (M <= 0 || N <= 0) return;
+        dim3 g((N + GN - 1) / GN, (M + GM - 1) / GM);
+        zgemm_sub_kernel<<<g, 256, 0, stream>>>(C, ld, A, ld, Bm, ld, M, N, K);
+        ++nl;
+    };
+    auto gemm2 = [&](z_t* C1, const z_t* B1, int N1, z_t* C2, const z_t* B2, int N2, const z_t* A, int M,
+                     int K) {
+        if (M <= 0) return;
+        const int nx1 = (N1 + GN - 1) / GN, nx2 = (N2 + GN - 1) / GN;
+        if (nx1 + nx2 == 0) return;
+        dim3 g(nx1 + nx2, (M + GM - 1) / GM);
+        zgemm_sub2_kernel<<<g, 256, 0, stream>>>(C1, B1, N1, nx1, C2, B2, N2, ld, A, M, K);
+        ++nl;
+    };
+
+    for (int K0 = 0; K0 < dim; K0 += NBO) {
+        const int JB = dim - K0 < NBO ? dim - K0 : NBO;
+        const int KE = K0 + JB;
+        // ---- factor the outer block column by NB-wide panels ----
+        for (int k0 = K0; k0 < KE; k0 += NB) {
+            int jb = KE - k0 < NB ? KE - k0 : NB;
+            const int ke = k0 + jb;
+            int rows = dim - k0;
+            int nblk = (rows + PT - 1) / PT;
+            if (optimistic) {
+                panel_nopiv_kernel<128><<<(rows + 127) / 128, 128, 0, stream>>>(W, ld, dim, k0, jb, g_tau,
+                                                                              d_flag, d_info);
+                e = cudaGetLastError();
+            } else if (rows <= CL_TPB * panel_cluster_limit() && !g_force_grid_panel) {
+                e = launch_panel_cluster(W, ld, dim, k0, jb, ipiv, d_info, stream);
+            } else {
+                int k0v = k0, dimv = dim, ldv = ld;
+                void* args[] = {&W, &ldv, &dimv, &k0v, &jb, &ipiv, &xchg, &d_info};
+                e = cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(nblk), dim3(PT), args, 0, stream);
+            }
+            if (e != cudaSuccess) return e;
+            ++nl;
+            if (k0 > K0 && !optimistic) {   // multipliers of the earlier panels follow their rows
+                laswp_kernel<<<(k0 - K0 + 127) / 128, 128, 0, stream>>>(at(W, 0, K0), k0 - K0, nullptr, 0,
+                                                                        ld, k0, jb, ipiv);
+                ++nl;
+            }
+            const int nin = KE - ke;
+            if (nin > 0) {
+                swap_trsm_kernel<<<(nin + 127) / 128, 128, 0, stream>>>(W, at(W, 0, ke), nin, nullptr, 0,
+                                                                        ld, k0, jb, ipiv, optimistic ? 0 : 1);
+                ++nl;
+                gemm1(at(W, ke, ke), at(W, ke, k0), at(W, k0, ke), dim - ke, nin, jb);
+            }
         }
+        // ---- the rest of W and all right-hand sides: interchanges, block-row solve, rank-JB update
+        const int nrest = dim - KE;
+        const int ncol = nrest + dim;
+        if (!optimistic) {
+            laswp_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(at(W, 0, KE), nrest, B, dim, ld, K0, JB, ipiv);
+            ++nl;
+        }
+        for (int k0 = K0; k0 < KE; k0 += NB) {
+            const int jb = KE - k0 < NB ? KE - k0 : NB;
+            const int ke = k0 + jb;
+            swap_trsm_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(W, at(W, 0, KE), nrest, B, dim, ld, k0,
+                                                                     jb, ipiv, 0);
+            ++nl;
+            gemm2(at(W, ke, KE), at(W, k0, KE), nrest, at(B, ke, 0), at(B, k0, 0), dim, at(W, ke, k0),
+                  KE - ke, jb);
+        }
+        gemm2(at(W, KE, KE), at(W, K0, KE), nrest, at(B, KE, 0), at(B, K0, 0), dim, at(W, KE, K0),
+              dim - KE, JB);
+    }
+    // ---- back substitution X = U^-1 Y, lower triangle of X only (the trace needs X_ii) ----
+    const int lastK = ((dim - 1) / NBO) * NBO;
+    for (int K0 = lastK; K0 >= 0; K0 -= NBO) {
+        const int JB = dim - K0 < NBO ? dim - K0 : NBO;
+        const int KE = K0 + JB;
+        const int lastk = K0 + ((JB - 1) / NB) * NB;
+        for (int k0 = lastk; k0 >= K0; k0 -= NB) {
+            const int jb = KE - k0 < NB ? KE - k0 : NB;
+            const int ke = k0 + jb;
+            utrsm_kernel<<<(ke + 127) / 128, 128, 0, stream>>>(W, B, ld, k0, jb, ke);
+            ++nl;
+            // rows of this outer block above the panel, columns [0, k0)
+            gemm1(at(B, K0, 0), at(W, K0, k0), at(B, k0, 0), k0 - K0, k0, jb);
+        }
+        // rows above the outer block, columns [0, K0)
+        gemm1(B, at(W, 0, K0), at(B, K0, 0), K0, K0, JB);
     }
     trace_kernel<<<1, 256, 0, stream>>>(B, ld, dim, (z_t*)d_trace);
     if (n_launches) *n_launches += nl + 1;

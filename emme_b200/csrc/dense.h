@@ -10,12 +10,17 @@ namespace emme {
 size_t dense_workspace_bytes(int dim);
 // trace(W^-1 B) -> *d_trace (double2 on device); W and B (dim x dim complex128, row-major)
 // are destroyed.  *d_info (device int): 0 or k > 0 if pivot k is exactly zero.
+// optimistic != 0: factor without row interchanges and raise *d_flag (device int) if partial
+// pivoting would have interchanged anything -- the caller must then repeat with optimistic = 0.
 cudaError_t launch_trace_solve(void* W, void* B, int dim, void* workspace, void* d_trace,
-                               int* d_info, cudaStream_t stream, unsigned long long* n_launches);
+                               int* d_info, cudaStream_t stream, unsigned long long* n_launches,
+                               int optimistic, int* d_flag);
+void dense_set_pivot_threshold(double tau);
 // Ad = (A - Aold)/delta over n complex entries
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,
                           double di, int sms, cudaStream_t stream);
 void dense_force_grid_panel(bool on);
+void dense_set_outer_block(int nbo);
 // measured DFMA throughput (TFLOP/s) of the current device
 cudaError_t measure_fp64_peak(double* tflops);
 }  // namespace emme

@@ -58,6 +58,7 @@ typedef struct emme_stats {
     double assemble_ms;           /* CUDA-event time of the last assembly kernel    */
     double dense_ms;              /* CUDA-event time of the last dense step         */
     unsigned long long launches;  /* kernels launched by this handle since creation */
+    unsigned long long pivot_fallbacks; /* dense steps repeated with row interchanges   */
 } emme_stats;
 
 typedef struct emme_solver emme_solver; /* opaque; owns device memory */

@@ -7,10 +7,18 @@ sys.path.insert(0, str(ROOT))
 from emme_b200 import EigenSolver, Input  # noqa: E402
 inp = Input(ROOT / "tests" / "golden" / "inputs" / "c1_n32.json")
 p, _ = inp.params()
-for n in [int(a) for a in sys.argv[1:]] or [1024]:
+kind = "dom"
+args = []
+for a in sys.argv[1:]:
+    if a in ("dom", "piv"):
+        kind = a
+    else:
+        args.append(int(a))
+for n in args or [1024]:
     rng = np.random.default_rng(n)
-    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * 0.05 + 2 * np.eye(n)
-    A[::7] *= 0.01
+    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * (0.5 / np.sqrt(n)) + 2 * np.eye(n)
+    if kind == "piv":
+        A[::7] *= 0.01          # badly scaled rows: partial pivoting must interchange
     B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     s = EigenSolver(p, n, np.linspace(-1, 1, n), np.zeros(n), np.ones(n))
     ms = []
@@ -22,5 +30,5 @@ for n in [int(a) for a in sys.argv[1:]] or [1024]:
         ref = -1.0 / np.trace(np.linalg.solve(A, B))
         err = abs(d - ref) / abs(ref)
     fl = (8 / 3 + 4 + 2) * n ** 3
-    print(f"n={n}: dense_ms min {min(ms):.3f}  {fl / min(ms) / 1e9:.2f} TFLOP/s  rel.err vs numpy {err}  launches/step {s.stats()['launches'] // 4}")
+    print(f"n={n}: dense_ms min {min(ms):.3f}  {fl / min(ms) / 1e9:.2f} TFLOP/s  rel.err vs numpy {err}  launches/step {s.stats()['launches'] // 4} fallbacks {s.stats()['pivot_fallbacks']} ({kind})")
     s.close()
