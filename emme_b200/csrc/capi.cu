@@ -59,6 +59,7 @@ struct emme_solver {
     unsigned long long launches = 0;
     int refill_min = 16;
     int optimistic = 1;               // try the interchange-free factorisation first
+    int null_optimistic = 1;
     unsigned long long pivot_fallbacks = 0;
     int* d_flag = nullptr;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
@@ -435,6 +436,71 @@ int emme_trace_delta(emme_solver* s, const void* host_A, const void* host_Ad, do
     if (dr) *dr = delta.real();
     if (di) *di = delta.imag();
     return rc;
+}
+
+// nullSpace (include/solver.h:58-112): the reference takes the right singular vector of the
+// smallest singular value from a full SVD (zgesdd) and conjugates it.  Here: inverse iteration
+// on A^H A with ONE LU factorisation of A.  A is complex symmetric, so A^H = conj(A) and
+//     (A^H A)^-1 v = A^-1 conj(A^-1 conj(v)).
+// The vector is defined up to a complex phase; it is normalised to unit 2-norm and rotated so
+// that its largest component is real positive.
+int emme_null_space(emme_solver* s, void* host_out) {
+    if (!s) return fail(-1, "null handle");
+    if (!host_out) return fail(-2, "null output");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_newton_buffers(s);
+    if (rc) return rc;
+    const int dim = s->dim;
+    // factor a copy of A (W) once; Ad serves as the right-hand-side / solution buffer
+    int info = 0, flag = 0;
+    for (int attempt = s->optimistic ? 0 : 1; attempt < 2; ++attempt) {
+        const int optimistic = attempt == 0;
+        CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
+        CU(emme::launch_trace_solve(s->W, s->Ad, dim, s->d_dense_ws, s->d_trace, s->d_info, s->stream,
+                                    &s->launches, optimistic, s->d_flag, 0));
+        CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));
+        if (optimistic)
+            CU(cudaMemcpyAsync(&flag, s->d_flag, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        s->null_optimistic = optimistic;
+        if (!optimistic || flag == 0) break;
+    }
+    if (info != 0) return fail(info, "nullSpace: matrix is exactly singular");
+    // start vector: all ones (deterministic), stored in column 0 of Ad
+    std::vector<zc> v(dim, zc(1.0 / std::sqrt((double)dim), 0.0));
+    CU(cudaMemcpy2DAsync(s->Ad, sizeof(zc) * dim, v.data(), sizeof(zc), sizeof(zc), dim,
+                         cudaMemcpyHostToDevice, s->stream));
+    double* d_norm = reinterpret_cast<double*>(s->d_trace);
+    double prev = 0.0;
+    for (int it = 0; it < 12; ++it) {
+        double nrm[2] = {0, 0};
+        for (int half = 0; half < 2; ++half) {
+            // rhs <- conj(rhs) happens inside the normalise kernel of the previous solve
+            CU(emme::launch_solve_factored(s->W, s->Ad, dim, 1, s->d_dense_ws, s->null_optimistic,
+                                           s->stream, &s->launches));
+            CU(emme::launch_conj_normalise(s->Ad, dim, dim, s->Ad, dim, d_norm, 1, s->stream));
+            ++s->launches;
+            CU(cudaMemcpyAsync(&nrm[half], d_norm, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        }
+        CU(cudaStreamSynchronize(s->stream));
+        // after two conj-solves the growth factor estimates 1/sigma_min^2
+        const double growth = nrm[0] * nrm[1];
+        if (it > 0 && std::fabs(growth - prev) <= 1e-13 * growth) break;
+        prev = growth;
+    }
+    // after an even number of conj-normalise passes column 0 holds conj(v); undo and fix the phase
+    CU(cudaMemcpy2DAsync(v.data(), sizeof(zc), s->Ad, sizeof(zc) * dim, sizeof(zc), dim,
+                         cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    size_t imax = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        v[i] = std::conj(v[i]);
+        if (std::abs(v[i]) > std::abs(v[imax])) imax = i;
+    }
+    const zc phase = std::conj(v[imax]) / std::abs(v[imax]);
+    for (auto& x : v) x *= phase;
+    std::memcpy(host_out, v.data(), sizeof(zc) * dim);
+    return 0;
 }
 
 void* emme_matrix_device_ptr(emme_solver* s, int which) {

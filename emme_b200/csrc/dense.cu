@@ -675,6 +675,78 @@ cudaError_t measure_fp64_peak(double* tflops) {
 static bool g_force_grid_panel = false;
 void dense_force_grid_panel(bool on) { g_force_grid_panel = on; }
 
+// Solve W X = B for nrhs right-hand sides (the first nrhs columns of the dim x dim buffer B,
+// overwritten by X) with the factors left in W by launch_trace_solve(..., nrhs >= 0) and the
+// interchanges recorded in the workspace.  Used by the inverse iteration of emme_null_space.
+cudaError_t launch_solve_factored(const void* Wv, void* Bv, int dim, int nrhs, void* workspace,
+                                  int optimistic, cudaStream_t stream, unsigned long long* n_launches) {
+    const z_t* W = (const z_t*)Wv;
+    z_t* B = (z_t*)Bv;
+    const int ld = dim;
+    const int nblk_max = (dim + PT - 1) / PT;
+    const int* ipiv = (const int*)((const char*)workspace + sizeof(PanelCand) * 2 * (size_t)nblk_max);
+    unsigned long long nl = 0;
+    for (int k0 = 0; k0 < dim; k0 += NB) {
+        const int jb = dim - k0 < NB ? dim - k0 : NB;
+        const int ke = k0 + jb;
+        swap_trsm_kernel<<<(nrhs + 127) / 128, 128, 0, stream>>>(W, B, nrhs, nullptr, 0, ld, k0, jb, ipiv,
+                                                                  optimistic ? 0 : 1);
+        ++nl;
+        const int M = dim - ke;
+        if (M > 0) {
+            dim3 g((nrhs + GN - 1) / GN, (M + GM - 1) / GM);
+            zgemm_sub_kernel<<<g, 256, 0, stream>>>(B + (size_t)ke * ld, ld, W + (size_t)ke * ld + k0, ld,
+                                                    B + (size_t)k0 * ld, ld, M, nrhs, jb);
+            ++nl;
+        }
+    }
+    const int last = ((dim - 1) / NB) * NB;
+    for (int k0 = last; k0 >= 0; k0 -= NB) {
+        const int jb = dim - k0 < NB ? dim - k0 : NB;
+        utrsm_kernel<<<(nrhs + 127) / 128, 128, 0, stream>>>(W, B, ld, k0, jb, nrhs);
+        ++nl;
+        if (k0 > 0) {
+            dim3 g((nrhs + GN - 1) / GN, (k0 + GM - 1) / GM);
+            zgemm_sub_kernel<<<g, 256, 0, stream>>>(B, ld, W + k0, ld, B + (size_t)k0 * ld, ld, k0, nrhs, jb);
+            ++nl;
+        }
+    }
+    if (n_launches) *n_launches += nl;
+    return cudaGetLastError();
+}
+
+// v <- conj(column 0 of X) scaled to unit 2-norm; X is dim x dim row-major (stride ld).
+// Also returns the norm (for convergence monitoring).  One block.
+__global__ void conj_normalise_kernel(const z_t* __restrict__ X, int ld, int dim, z_t* __restrict__ rhs,
+                                      int rhs_ld, double* __restrict__ norm_out, int conjugate) {
+    __shared__ double sh[256];
+    double acc = 0.;
+    for (int i = threadIdx.x; i < dim; i += 256) {
+        const z_t v = X[(size_t)i * ld];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double nrm = sqrt(sh[0]);
+    const double inv = nrm > 0. ? 1.0 / nrm : 0.;
+    for (int i = threadIdx.x; i < dim; i += 256) {
+        const z_t v = X[(size_t)i * ld];
+        rhs[(size_t)i * rhs_ld] = make_double2(v.x * inv, conjugate ? -v.y * inv : v.y * inv);
+    }
+    if (threadIdx.x == 0 && norm_out) *norm_out = nrm;
+}
+
+cudaError_t launch_conj_normalise(const void* X, int ld, int dim, void* rhs, int rhs_ld, double* norm_out,
+                                  int conjugate, cudaStream_t stream) {
+    conj_normalise_kernel<<<1, 256, 0, stream>>>((const z_t*)X, ld, dim, (z_t*)rhs, rhs_ld, norm_out,
+                                                 conjugate);
+    return cudaGetLastError();
+}
+
 size_t dense_workspace_bytes(int dim) {
     const int nblk = (dim + PT - 1) / PT;
     return sizeof(PanelCand) * 2 * (size_t)nblk + sizeof(int) * (size_t)dim + 64;
@@ -695,8 +767,10 @@ void dense_set_pivot_threshold(double tau) { g_tau = tau; }
 // FP64 pipe busy; K = 32 was dominated by the C-tile read-modify-write).
 cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, void* d_trace,
                                int* d_info, cudaStream_t stream, unsigned long long* n_launches,
-                               int optimistic, int* d_flag) {
+                               int optimistic, int* d_flag, int nrhs) {
     unsigned long long nl = 0;
+    const bool want_trace = nrhs < 0;      // nrhs < 0: all dim right-hand sides + trace
+    if (nrhs < 0) nrhs = dim;
     z_t* W = (z_t*)Wv;
     z_t* B = (z_t*)Bv;
     const int ld = dim;
@@ -765,22 +839,27 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
         }
         // ---- the rest of W and all right-hand sides: interchanges, block-row solve, rank-JB update
         const int nrest = dim - KE;
-        const int ncol = nrest + dim;
+        const int ncol = nrest + nrhs;
+        if (ncol == 0) continue;
         if (!optimistic) {
-            laswp_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(at(W, 0, KE), nrest, B, dim, ld, K0, JB, ipiv);
+            laswp_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(at(W, 0, KE), nrest, B, nrhs, ld, K0, JB, ipiv);
             ++nl;
         }
         for (int k0 = K0; k0 < KE; k0 += NB) {
             const int jb = KE - k0 < NB ? KE - k0 : NB;
             const int ke = k0 + jb;
-            swap_trsm_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(W, at(W, 0, KE), nrest, B, dim, ld, k0,
+            swap_trsm_kernel<<<(ncol + 127) / 128, 128, 0, stream>>>(W, at(W, 0, KE), nrest, B, nrhs, ld, k0,
                                                                      jb, ipiv, 0);
             ++nl;
-            gemm2(at(W, ke, KE), at(W, k0, KE), nrest, at(B, ke, 0), at(B, k0, 0), dim, at(W, ke, k0),
+            gemm2(at(W, ke, KE), at(W, k0, KE), nrest, at(B, ke, 0), at(B, k0, 0), nrhs, at(W, ke, k0),
                   KE - ke, jb);
         }
-        gemm2(at(W, KE, KE), at(W, K0, KE), nrest, at(B, KE, 0), at(B, K0, 0), dim, at(W, KE, K0),
+        gemm2(at(W, KE, KE), at(W, K0, KE), nrest, at(B, KE, 0), at(B, K0, 0), nrhs, at(W, KE, K0),
               dim - KE, JB);
+    }
+    if (!want_trace) {
+        if (n_launches) *n_launches += nl;
+        return cudaGetLastError();
     }
     // ---- back substitution X = U^-1 Y, lower triangle of X only (the trace needs X_ii) ----
     const int lastK = ((dim - 1) / NBO) * NBO;

@@ -14,7 +14,14 @@ size_t dense_workspace_bytes(int dim);
 // pivoting would have interchanged anything -- the caller must then repeat with optimistic = 0.
 cudaError_t launch_trace_solve(void* W, void* B, int dim, void* workspace, void* d_trace,
                                int* d_info, cudaStream_t stream, unsigned long long* n_launches,
-                               int optimistic, int* d_flag);
+                               int optimistic, int* d_flag, int nrhs = -1);
+// nrhs < 0 (default): all dim right-hand sides, back substitution and trace.
+// nrhs >= 0: factor W and forward-eliminate only the first nrhs columns of B; no back
+// substitution -- follow with launch_solve_factored for complete solves against the factors.
+cudaError_t launch_solve_factored(const void* W, void* B, int dim, int nrhs, void* workspace,
+                                  int optimistic, cudaStream_t stream, unsigned long long* n_launches);
+cudaError_t launch_conj_normalise(const void* X, int ld, int dim, void* rhs, int rhs_ld, double* norm_out,
+                                  int conjugate, cudaStream_t stream);
 void dense_set_pivot_threshold(double tau);
 // Ad = (A - Aold)/delta over n complex entries
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,

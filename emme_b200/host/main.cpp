@@ -1,0 +1,220 @@
+// main.cpp -- the `emme` host program of emme_b200: same input, same outputs as the reference's
+// main() (src/main.cpp:182-338), with the eigen hot path on the GPU through the C ABI.
+//
+//   reads   ./input.json                                   (src/main.cpp:183-184)
+//   writes  ./output.json, ./eigenMatrics/*.bin            (src/main.cpp:255-257,295-299,327-330)
+//   prints  one line per Newton iterate, the eigenvalue, a timing table
+//
+// Scan objects {head, step, tail} follow the reference's generator and its continuation of omega
+// between scan points (src/main.cpp:139-172,262-325); a failing point is recorded as
+// {"eigenvalue": "NaN", "reason": ...} and the scan continues (src/main.cpp:300-318).
+// Only method "eigen" with iteration_method "TraceSecant" is implemented;
+// anything else raises the reference's "not supported" error text.
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "eigen_solver.hpp"
+#include "json.hpp"
+#include "parameters.hpp"
+
+using emme::json::Value;
+using clk = std::chrono::steady_clock;
+
+namespace {
+
+// named wall-clock accumulators with the reference's category names (src/Timer.cpp)
+struct Timers {
+    std::vector<std::string> order;
+    std::unordered_map<std::string, double> total;
+    std::unordered_map<std::string, clk::time_point> start;
+    void begin(const std::string& n) {
+        if (!total.count(n)) { total[n] = 0; order.push_back(n); }
+        start[n] = clk::now();
+    }
+    void end(const std::string& n) {
+        total[n] += std::chrono::duration<double>(clk::now() - start[n]).count();
+    }
+    void print() const {
+        std::cout << "  " << std::left << std::setw(20) << "timer" << "seconds\n";
+        for (const auto& n : order)
+            std::cout << "  " << std::left << std::setw(20) << n << total.at(n) << '\n';
+    }
+} timers;
+
+std::string date_string() {   // ISO 8601 with a colon in the zone offset, like util::get_date_string
+    std::time_t t = std::time(nullptr);
+    std::tm tm = *std::localtime(&t);
+    std::ostringstream ss;
+    ss << std::put_time(&tm, "%FT%T%z");
+    std::string s = ss.str();
+    if (s.size() > 5 && (s[s.size() - 5] == '+' || s[s.size() - 5] == '-')) s.insert(s.size() - 2, ":");
+    return s;
+}
+
+Value solve_once_eigen(const Value& input, std::complex<double>& omega_initial_guess,
+                       std::ofstream& eigen_matrix_file) {
+    const double tol = input.at("iteration_precision");
+    timers.begin("initial");
+    auto para = emme::Parameters::generate(input);
+    emme::EigenSolver solver(*para, omega_initial_guess);
+    timers.end("initial");
+    const std::string iter_method = input.at("iteration_method").as_string();
+    if (iter_method != "TraceSecant")
+        throw std::runtime_error("iteration_method '" + iter_method +
+                                 "' is not supported by emme_b200 (TraceSecant only).");
+    for (int j = 0; j <= para->iteration_step_limit; j++) {
+        timers.begin("Iteration");
+        solver.newtonTraceSecantIteration();
+        timers.end("Iteration");
+        std::cout << "        " << solver.eigen_value << '\n';
+        if (std::abs(solver.d_eigen_value) < std::abs(tol * solver.eigen_value)) break;
+    }
+    std::cout << "        Eigenvalue: " << solver.eigen_value << '\n';
+    timers.begin("Output");
+    const auto& m = solver.eigen_matrix();
+    eigen_matrix_file.write(reinterpret_cast<const char*>(m.data()),
+                            sizeof(std::complex<double>) * m.size());
+    Value single = Value::object();
+    Value ev = Value::array(2);
+    ev[0] = Value(solver.eigen_value.real());
+    ev[1] = Value(solver.eigen_value.imag());
+    single["eigenvalue"] = ev;
+    timers.end("Output");
+    timers.begin("SVD");
+    single["eigenvector"] = Value::complex_array(solver.nullSpace());
+    timers.end("SVD");
+    omega_initial_guess = solver.eigen_value;
+    return single;
+}
+
+// get_scan_generator (src/main.cpp:139-172) as a stateful object
+struct ScanGenerator {
+    double head, step, left_tail, right_tail, current, current_tail;
+    bool to_left = true, is_first = true;
+    explicit ScanGenerator(const std::array<double, 4>& p)
+        : head(p[0]), step(p[1]), left_tail(p[2]), right_tail(p[3]), current(p[0]), current_tail(p[2]) {}
+    bool within() const {
+        return std::abs(current - head) <= (std::abs(current_tail - head) + 0.01 * std::abs(step));
+    }
+    // (continue, turning, value)
+    std::tuple<bool, bool, double> next() {
+        if (!is_first) current += std::copysign(step, current_tail - head);
+        is_first = false;
+        if (within()) return {true, false, current};
+        to_left = !to_left;
+        current_tail = right_tail;
+        current = head + std::copysign(step, current_tail - head);
+        return {!to_left && within(), true, current};
+    }
+};
+
+Value filter_input(const Value& all) {
+    Value in = all.clone();
+    for (auto& [key, val] : in.as_object())
+        if (val.is_object()) { Value h = val.at("head"); val = h; }
+    return in;
+}
+
+}  // namespace
+
+int main() {
+    const std::string filename = "input.json";
+    Value input_all = emme::json::parse_file(filename);
+    auto invoke_solver = [&](const Value& in, std::complex<double>& w, std::ofstream& f) {
+        const std::string method = input_all.at("method").as_string();
+        if (method == "eigen") return solve_once_eigen(in, w, f);
+        throw std::runtime_error("Method '" + method + "' is not supported, yet.\n");
+    };
+    timers.begin("All");
+    std::complex<double> omega_initial_guess(input_all.at("initial_guess").at(0).number(),
+                                             input_all.at("initial_guess").at(1).number());
+    Value result = Value::object();
+    result["input"] = input_all.clone();
+    result["run_time"] = Value(date_string());
+
+    std::unordered_map<std::string, std::array<double, 4>> scan_config;
+    for (const auto& [key, val] : input_all.as_object()) {
+        if (!val.is_object()) continue;
+        std::array<double, 4> p{val.at("head").number(), val.at("step").number(), 0, 0};
+        if (val.at("tail").is_array()) {
+            p[2] = val.at("tail").at(0).number();
+            p[3] = val.at("tail").at(1).number();
+        } else {
+            p[2] = val.at("tail").number();
+            p[3] = p[0] + .5 * std::copysign(p[1], p[0] - p[2]);
+        }
+        scan_config.emplace(key, p);
+    }
+
+    Value result_object = Value::object();
+    if (scan_config.empty()) {
+        Value unit = Value::object();
+        unit["scan_key"] = Value("(None)");
+        Value arr = Value::array();
+        std::cout << '\n';
+        std::ofstream f("eigenMatrics/eigenMatrix.bin", std::ios::binary);
+        arr.as_array().push_back(invoke_solver(input_all, omega_initial_guess, f));
+        unit["scan_result"] = arr;
+        result_object["(None)"] = unit;
+    } else {
+        auto omega = omega_initial_guess;
+        for (const auto& [key, scan_para] : scan_config) {
+            Value input = filter_input(input_all);
+            ScanGenerator gen(scan_para);
+            auto [cont, turning, scan_value] = gen.next();
+            Value unit = Value::object();
+            unit["scan_key"] = Value(key);
+            Value values = Value::array();
+            Value results = Value::array();
+            std::cout << "\nScanning " << key << '\n';
+            while (cont) {
+                input[key] = Value(scan_value);
+                values.as_array().push_back(Value(scan_value));
+                if (turning) {   // the other direction restarts from the first point's eigenvalue
+                    const Value& first = results.as_array().at(0).at("eigenvalue");
+                    if (first.is_string()) omega = omega_initial_guess;
+                    else omega = {first.at(0).number(), first.at(1).number()};
+                }
+                std::cout << "    " << key << ":" << scan_value << '\n';
+                const std::string fname = "eigenMatrics/" + key + "Eq" + std::to_string(scan_value) + ".bin";
+                std::ofstream f(fname, std::ios::binary);
+                try {
+                    Value single = invoke_solver(input, omega, f);
+                    single["eigenMatrix"] = Value(f ? fname : "Can not open '" + fname + "' for write.");
+                    single["scan_value"] = Value(scan_value);
+                    results.as_array().push_back(single);
+                } catch (const std::exception& e) {
+                    Value err = Value::object();
+                    err["eigenvalue"] = Value("NaN");
+                    err["reason"] = Value(e.what());
+                    results.as_array().push_back(err);
+                    std::cerr << "        " << e.what() << '\n';
+                }
+                std::tie(cont, turning, scan_value) = gen.next();
+            }
+            unit["scan_values"] = values;
+            unit["scan_result"] = results;
+            result_object[key] = unit;
+            omega = omega_initial_guess;
+        }
+    }
+    result["result"] = result_object;
+    timers.begin("Output");
+    std::ofstream("output.json") << result.pretty_print();
+    timers.end("Output");
+    timers.end("All");
+    std::cout << '\n';
+    timers.print();
+    std::cout << '\n';
+    return 0;
+}

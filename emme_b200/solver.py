@@ -146,6 +146,13 @@ class EigenSolver:
                                               C.byref(dr), C.byref(di)))
         return complex(dr.value, di.value)
 
+    def nullSpace(self):
+        """Eigenvector of the current eigen_matrix (include/solver.h:58-112), unit 2-norm, largest
+        component real positive."""
+        v = np.empty(self.dim, dtype=np.complex128)
+        capi.check(self._lib.emme_null_space(self._h, v.ctypes.data))
+        return v
+
     def _matrix(self, which):
         out = np.empty((self.dim, self.dim), dtype=np.complex128)
         capi.check(self._lib.emme_copy_matrix(self._h, which, out.ctypes.data))

@@ -127,6 +127,13 @@ int emme_step_begin(emme_solver* s);                           /* dense step, om
 int emme_step_finish(emme_solver* s, double* wr, double* wi, double* dr, double* di);
 void* emme_matrix_device_ptr(emme_solver* s, int which);
 
+/* EigenSolver::nullSpace (include/solver.h:58-112): the eigenvector, i.e. the right singular
+ * vector of eigen_matrix for its smallest singular value (dim complex128 to host_out), by
+ * inverse iteration on one LU factorisation instead of the reference's full SVD (zgesdd).
+ * Normalised to unit 2-norm with the largest component real positive (the reference's vector
+ * carries LAPACK's arbitrary phase).  Overwrites eigen_matrix_derivative. */
+int emme_null_space(emme_solver* s, void* host_out);
+
 /* which: 0 = eigen_matrix, 1 = eigen_matrix_old, 2 = eigen_matrix_derivative
  * (the three public matrices of EigenSolver, include/solver.h:392-394). */
 int emme_copy_matrix(emme_solver* s, int which, void* host_out);

@@ -126,3 +126,34 @@ def test_no_cpu_fallback(native_lib):
     with pytest.raises(EmmeError, match="no CPU fallback") as ei:
         EigenSolver.from_input(inp)
     assert ei.value.code == capi.E_NO_DEVICE
+
+
+def _run_emme(tmp_path, input_text):
+    import subprocess
+    from emme_b200 import build
+    build.build_all()
+    (tmp_path / "input.json").write_text(input_text)
+    (tmp_path / "eigenMatrics").mkdir(exist_ok=True)
+    return subprocess.run([str(build.EXE)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+
+
+def test_host_program_fails_loudly_without_gpu(tmp_path, native_lib):
+    """The C++ host program (mirror of the reference's main) must not fall back to the CPU:
+    a single solve aborts, a scan records every point as NaN with the reason (src/main.cpp:300-318)."""
+    if native_lib.emme_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = _run_emme(tmp_path, cases.input_path("c1_n32").read_text())
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+    scan = cases.input_path("c1_n32").read_text().replace(
+        '"omega_d_coeff": 1.0', '"omega_d_coeff": {"head": 1.0, "step": 0.25, "tail": 0.5}')
+    r = _run_emme(tmp_path, scan)
+    assert r.returncode == 0, r.stderr
+    out = Input(tmp_path / "output.json")          # our own reader parses what the writer wrote
+    txt = (tmp_path / "output.json").read_text()
+    assert txt.count('"eigenvalue": "NaN"') == 3 and "no CPU fallback" in txt
+    assert '"scan_key": "omega_d_coeff"' in txt
+
+
+def test_host_program_rejects_pic(tmp_path, native_lib):
+    r = _run_emme(tmp_path, cases.input_path("c1_n32").read_text().replace('"method": "eigen"', '"method": "PIC"'))
+    assert r.returncode != 0 and "Method 'PIC' is not supported, yet." in r.stderr

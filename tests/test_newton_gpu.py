@@ -78,3 +78,61 @@ def test_step_before_seed_is_an_error(native_lib):
     with pytest.raises(EmmeError) as ei:
         s.newtonTraceSecantIteration()
     assert ei.value.code == capi.E_STATE
+
+
+def test_null_space_matches_svd(native_lib):
+    """nullSpace (include/solver.h:58-112): right singular vector of the smallest singular value,
+    compared with numpy's SVD of the same matrix up to the arbitrary complex phase."""
+    inp = Input(cases.input_path("c1_n128"))
+    w, iters, s = solve_once_eigen(inp, inp.initial_guess())
+    A = s.eigen_matrix
+    v = s.nullSpace()
+    _, sv, vh = np.linalg.svd(A)
+    ref = np.conj(vh[-1])
+    assert abs(np.linalg.norm(v) - 1) < 1e-12
+    overlap = abs(np.vdot(ref, v))
+    print(f"\n[nullspace] sigma_min={sv[-1]:.3e} sigma_2={sv[-2]:.3e} |<ref,v>|={overlap:.15f}")
+    assert overlap > 1 - 1e-9
+    assert np.linalg.norm(A @ v) <= 1.0000001 * sv[-1] + 1e-14
+    k = np.argmax(np.abs(v))
+    assert abs(v[k].imag) < 1e-14 and v[k].real > 0
+
+
+def test_host_program_end_to_end(tmp_path, golden, native_lib):
+    """The C++ `emme` program on input.json -> output.json + eigenMatrics/eigenMatrix.bin."""
+    import re
+    import subprocess
+    from emme_b200 import build
+    build.build_all()
+    (tmp_path / "input.json").write_text(cases.input_path("c1_n64").read_text())
+    (tmp_path / "eigenMatrics").mkdir()
+    r = subprocess.run([str(build.EXE)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rec = golden["newton"]["c1_n64"]
+    assert r.stdout.count("        (") == rec["final"][2]                 # one line per iterate
+    out = (tmp_path / "output.json").read_text()
+    m = re.search(r'"eigenvalue": \[\s*([-0-9.e]+),\s*([-0-9.e]+)', out)
+    assert abs(float(m.group(1)) - rec["final"][0]) < 1e-5 and abs(float(m.group(2)) - rec["final"][1]) < 1e-5
+    assert '"scan_key": "(None)"' in out and '"eigenvector"' in out
+    A = np.fromfile(tmp_path / "eigenMatrics" / "eigenMatrix.bin", dtype=np.complex128).reshape(64, 64)
+    assert np.array_equal(A, A.T) and np.all(np.diag(A) == 2.0)
+
+
+def test_pivoting_fallback_is_taken_and_correct(native_lib):
+    """A matrix that needs row interchanges: the optimistic factorisation must raise its flag and
+    the step must be repeated with partial pivoting (stats.pivot_fallbacks counts it)."""
+    rng = np.random.default_rng(5)
+    n = 200
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    inp = Input(cases.input_path("c1_n32"))
+    p, _ = inp.params()
+    s = EigenSolver(p, n, np.linspace(-1, 1, n), np.zeros(n), np.ones(n))
+    d = s.trace_delta(A, B)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    assert abs(d - ref) <= 1e-10 * abs(ref)
+    assert s.stats()["pivot_fallbacks"] == 1
+    D = A * 0.01 + 3 * np.eye(n)
+    d = s.trace_delta(D, B)
+    assert abs(d + 1.0 / np.trace(np.linalg.solve(D, B))) <= 1e-12 * abs(d)
+    assert s.stats()["pivot_fallbacks"] == 1          # diagonally dominant: no fallback
