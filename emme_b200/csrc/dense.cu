@@ -481,89 +481,126 @@ utrsm_kernel(const z_t* __restrict__ W, z_t* __restrict__ B, int ld, int k0, int
 // C[M x N] -= A[M x K] * Bm[K x N], all row-major with their own leading dimensions.
 // 64x64 tile per CTA, 256 threads, 4x4 complex accumulators per thread, K slabs of 16 staged
 // through shared memory.  FP64-pipe bound by construction (64 DFMA per 8 LDS.128).
-constexpr int GM = 64, GN = 64, GK = 8;
+constexpr int GM = 64, GN = 64, GK = 16, GSTAGES = 3;
+constexpr int G_LDA = GK + 4;    // sA[m][k]: row stride = 4 (mod 8) elements -> conflict-free fragment loads
+constexpr int G_LDB = GN + 2;    // sB[k][n]: row stride = 2 (mod 8) elements
+constexpr int G_STAGE_ELEMS = GM * G_LDA + GK * G_LDB;                  // z_t per pipeline stage
+constexpr size_t G_SMEM_BYTES = sizeof(z_t) * G_STAGE_ELEMS * GSTAGES;  // 110 KB: 2 CTAs per SM
 
-// Software-pipelined: while the DFMAs of k-slab s run out of shared memory, the global loads of
-// slab s+1 are in flight into registers; one __syncthreads per slab (double-buffered smem).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = pred ? 16 : 0;   // src-size 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// FP64 tensor-core multiply-accumulate: D(8x8) += A(8x4) * B(4x8)   (SASS: DMMA.8x8x4)
+// lane T holds A[T/4][T%4], B[T%4][T/4] and D[T/4][2*(T%4) + {0,1}].
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+// C[M x N] -= A[M x K] * Bm[K x N] on one 64x64 complex tile (256 threads = 8 warps, 4 x 2, each
+// warp a 16 x 32 sub-tile = 2 x 4 DMMA blocks).  The complex product is four real tensor-core
+// products per block (re*re, -im*im, re*im, im*re) on the interleaved (re, im) data: one 16-byte
+// shared-memory load delivers both fragment values.  On B200 the FP64 tensor rate equals the DFMA
+// rate (37 TFLOP/s measured for both), but a DMMA carries 256 FMAs per issue slot instead of 32,
+// so the FP64 pipe stays fed (the DFMA version of this tile stalled at 60-64 % pipe utilisation).
+// k-slabs of 16 travel global -> shared memory with cp.async through a 3-stage ring.
 __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
                                                const z_t* __restrict__ A, int lda,
                                                const z_t* __restrict__ Bm, int ldb, int M, int N,
                                                int K, int bx, int by) {
-    __shared__ z_t sA[2][GK][GM + 1];
-    __shared__ z_t sB[2][GK][GN];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    extern __shared__ __align__(16) unsigned char g_smem_raw[];
+    z_t* smem = reinterpret_cast<z_t*>(g_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;          // warp grid 4 (M) x 2 (N)
     const int m0 = by * GM, n0 = bx * GN;
-    // element ownership for the global->shared staging (2 of A, 2 of B per thread)
-    const int am = threadIdx.x >> 3, ak = threadIdx.x & 7;          // A: rows am, am+32; col ak
-    const int bk = threadIdx.x >> 6, bn = threadIdx.x & 63;         // B: rows bk, bk+4;  col bn
-    const bool a_ok0 = m0 + am < M, a_ok1 = m0 + am + 32 < M, b_ok = n0 + bn < N;
-    const z_t* Ap0 = A + (size_t)(m0 + am) * lda + ak;
-    const z_t* Ap1 = A + (size_t)(m0 + am + 32) * lda + ak;
-    const z_t* Bp0 = Bm + (size_t)bk * ldb + n0 + bn;
-    const z_t* Bp1 = Bm + (size_t)(bk + 4) * ldb + n0 + bn;
-    const z_t zero = make_double2(0., 0.);
-
-    z_t acc[4][4];
+    // staging ownership: A slab = 64 rows x 16 k, B slab = 16 k x 64 cols; 4 + 4 elements/thread
+    const int ak = threadIdx.x & 15, am = threadIdx.x >> 4;      // A: rows am, am+16, am+32, am+48
+    const int bn = threadIdx.x & 63, bk = threadIdx.x >> 6;      // B: k rows bk, bk+4, bk+8, bk+12
+    auto issue = [&](int slab) {
+        z_t* sA = smem + (size_t)(slab % GSTAGES) * G_STAGE_ELEMS;   // [GM][G_LDA]
+        z_t* sB = sA + GM * G_LDA;                                   // [GK][G_LDB]
+        const int kk = slab * GK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int e = 0; e < 4; ++e) {
+            const int m = am + 16 * e;
+            const bool ok = (m0 + m < M) && (kk + ak < K);
+            const z_t* src = ok ? A + (size_t)(m0 + m) * lda + kk + ak : A;
+            cp_async16(sA + m * G_LDA + ak, src, ok);
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = zero;
-
-    z_t ra0, ra1, rb0, rb1;
-    auto fetch = [&](int kk) {
-        ra0 = (a_ok0 && kk + ak < K) ? Ap0[kk] : zero;
-        ra1 = (a_ok1 && kk + ak < K) ? Ap1[kk] : zero;
-        rb0 = (b_ok && kk + bk < K) ? Bp0[(size_t)kk * ldb] : zero;
-        rb1 = (b_ok && kk + bk + 4 < K) ? Bp1[(size_t)kk * ldb] : zero;
+        for (int e = 0; e < 4; ++e) {
+            const int k = bk + 4 * e;
+            const bool ok = (kk + k < K) && (n0 + bn < N);
+            const z_t* src = ok ? Bm + (size_t)(kk + k) * ldb + n0 + bn : Bm;
+            cp_async16(sB + k * G_LDB + bn, src, ok);
+        }
     };
-    auto stage = [&](int buf) {
-        sA[buf][ak][am] = ra0;
-        sA[buf][ak][am + 32] = ra1;
-        sB[buf][bk][bn] = rb0;
-        sB[buf][bk + 4][bn] = rb1;
-    };
-    fetch(0);
-    stage(0);
-    __syncthreads();
-    int buf = 0;
-    for (int kk = 0; kk < K; kk += GK) {
-        const bool more = kk + GK < K;
-        if (more) fetch(kk + GK);
+    double acc_re[2][4][2], acc_im[2][4][2];
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            z_t av[4], bv[4];
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = sA[buf][k][ty * 4 + i];
+        for (int j = 0; j < 4; ++j) {
+            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
+            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+        }
+
+    const int nslab = (K + GK - 1) / GK;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = sB[buf][k][tx + 16 * j];
+    for (int s0 = 0; s0 < GSTAGES - 1; ++s0) {
+        if (s0 < nslab) issue(s0);
+        cp_async_commit();
+    }
+    for (int slab = 0; slab < nslab; ++slab) {
+        cp_async_wait<GSTAGES - 2>();
+        __syncthreads();   // slab `slab` has landed for every thread; slab-1's buffer is free
+        if (slab + GSTAGES - 1 < nslab) issue(slab + GSTAGES - 1);
+        cp_async_commit();
+        const z_t* sA = smem + (size_t)(slab % GSTAGES) * G_STAGE_ELEMS;
+        const z_t* sB = sA + GM * G_LDA;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            z_t af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = sA[(wm * 16 + i * 8 + g) * G_LDA + k4 + q];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = sB[(k4 + q) * G_LDB + wn * 32 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double nai = -af[i].y;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    acc[i][j].x = fma(av[i].x, bv[j].x, acc[i][j].x);
-                    acc[i][j].x = fma(-av[i].y, bv[j].y, acc[i][j].x);
-                    acc[i][j].y = fma(av[i].x, bv[j].y, acc[i][j].y);
-                    acc[i][j].y = fma(av[i].y, bv[j].x, acc[i][j].y);
+                    dmma(acc_re[i][j], af[i].x, bf[j].x);
+                    dmma(acc_im[i][j], af[i].x, bf[j].y);
+                    dmma(acc_re[i][j], nai, bf[j].y);
+                    dmma(acc_im[i][j], af[i].y, bf[j].x);
                 }
-        }
-        if (more) {
-            stage(buf ^ 1);
-            __syncthreads();
-            buf ^= 1;
+            }
         }
     }
+    cp_async_wait<0>();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + wm * 16 + i * 8 + g;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx + 16 * j;
-            if (n >= N) continue;
-            z_t c = C[(size_t)m * ldc + n];
-            c.x -= acc[i][j].x;
-            c.y -= acc[i][j].y;
-            C[(size_t)m * ldc + n] = c;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * q + e;
+                if (n >= N) continue;
+                z_t c = C[(size_t)m * ldc + n];
+                c.x -= acc_re[i][j][e];
+                c.y -= acc_im[i][j][e];
+                C[(size_t)m * ldc + n] = c;
+            }
         }
     }
 }
@@ -585,6 +622,19 @@ zgemm_sub2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int N1, int 
         zgemm_sub_tile(C1, ld, A, ld, B1, ld, M, N1, K, blockIdx.x, blockIdx.y);
     else
         zgemm_sub_tile(C2, ld, A, ld, B2, ld, M, N2, K, blockIdx.x - nx1, blockIdx.y);
+}
+
+static cudaError_t gemm_setup() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zgemm_sub2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)G_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -686,6 +736,10 @@ cudaError_t launch_solve_factored(const void* Wv, void* Bv, int dim, int nrhs, v
     const int nblk_max = (dim + PT - 1) / PT;
     const int* ipiv = (const int*)((const char*)workspace + sizeof(PanelCand) * 2 * (size_t)nblk_max);
     unsigned long long nl = 0;
+    {
+        cudaError_t e = gemm_setup();
+        if (e != cudaSuccess) return e;
+    }
     for (int k0 = 0; k0 < dim; k0 += NB) {
         const int jb = dim - k0 < NB ? dim - k0 : NB;
         const int ke = k0 + jb;
@@ -695,8 +749,9 @@ cudaError_t launch_solve_factored(const void* Wv, void* Bv, int dim, int nrhs, v
         const int M = dim - ke;
         if (M > 0) {
             dim3 g((nrhs + GN - 1) / GN, (M + GM - 1) / GM);
-            zgemm_sub_kernel<<<g, 256, 0, stream>>>(B + (size_t)ke * ld, ld, W + (size_t)ke * ld + k0, ld,
-                                                    B + (size_t)k0 * ld, ld, M, nrhs, jb);
+            zgemm_sub_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(B + (size_t)ke * ld, ld,
+                                                               W + (size_t)ke * ld + k0, ld,
+                                                               B + (size_t)k0 * ld, ld, M, nrhs, jb);
             ++nl;
         }
     }
@@ -707,7 +762,8 @@ cudaError_t launch_solve_factored(const void* Wv, void* Bv, int dim, int nrhs, v
         ++nl;
         if (k0 > 0) {
             dim3 g((nrhs + GN - 1) / GN, (k0 + GM - 1) / GM);
-            zgemm_sub_kernel<<<g, 256, 0, stream>>>(B, ld, W + k0, ld, B + (size_t)k0 * ld, ld, k0, nrhs, jb);
+            zgemm_sub_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(B, ld, W + k0, ld, B + (size_t)k0 * ld, ld, k0,
+                                                               nrhs, jb);
             ++nl;
         }
     }
@@ -777,7 +833,9 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
     const int nblk_max = (dim + PT - 1) / PT;
     PanelCand* xchg = (PanelCand*)workspace;
     int* ipiv = (int*)((char*)workspace + sizeof(PanelCand) * 2 * (size_t)nblk_max);
-    cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), stream);
+    cudaError_t e = gemm_setup();
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d_info, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
     // small systems are latency bound: single-level blocking means fewer launches
     const int NBO = g_nbo > 0 ? g_nbo : (dim <= 2048 ? NB : 128);
@@ -789,7 +847,7 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
     auto gemm1 = [&](z_t* C, const z_t* A, const z_t* Bm, int M, int N, int K) {
         if (M <= 0 || N <= 0) return;
         dim3 g((N + GN - 1) / GN, (M + GM - 1) / GM);
-        zgemm_sub_kernel<<<g, 256, 0, stream>>>(C, ld, A, ld, Bm, ld, M, N, K);
+        zgemm_sub_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(C, ld, A, ld, Bm, ld, M, N, K);
         ++nl;
     };
     auto gemm2 = [&](z_t* C1, const z_t* B1, int N1, z_t* C2, const z_t* B2, int N2, const z_t* A, int M,
@@ -798,7 +856,7 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
         const int nx1 = (N1 + GN - 1) / GN, nx2 = (N2 + GN - 1) / GN;
         if (nx1 + nx2 == 0) return;
         dim3 g(nx1 + nx2, (M + GM - 1) / GM);
-        zgemm_sub2_kernel<<<g, 256, 0, stream>>>(C1, B1, N1, nx1, C2, B2, N2, ld, A, M, K);
+        zgemm_sub2_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(C1, B1, N1, nx1, C2, B2, N2, ld, A, M, K);
         ++nl;
     };
 
