@@ -60,6 +60,7 @@ struct RunConst {
     double qR;          // q*R
     double vt;
     double arc;         // arc_coeff
+    double inv_arc;     // 1/arc_coeff
     double omega_s_i;
     double eta_i;
     double wsi_etai;    // omega_s_i*eta_i
@@ -161,7 +162,9 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
         ++n;
     }
     cnt.fwd += (unsigned)(n - n0);
-    y0 = recip(pb);
+    // the reference starts the backward pass from 1/p_N; the returned ratios y/mu do not depend
+    // on that scale (everything is linear in it), so the complex reciprocal is dropped
+    y0 = mk(1., 0.);
     y1 = mk(0., 0.);
     mu = mk(0., 0.);
     --n;
@@ -186,19 +189,20 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
 // g(x) for mode m (0, 1, 2).  x in (0, pi/2).
 EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
                        EvalCounters& cnt) {
-    // t = tan x and cos x from one sincos (include/functions.h:316-317)
+    // t = tan x, 1/t and 1/cos^2 x from one sincos and two reciprocals (include/functions.h:316-317)
     double sx, c;
     sincos(x, &sx, &c);
-    const double t = sx / c;
+    const double ic = 1.0 / c, it = c / sx;
+    const double t = sx * ic;
     // contour rotation e = exp(-i*omi*atan(u)), u = t/arc, tau~ = t*e (src/Parameters.cpp:121-124):
     // cos(atan u) = 1/sqrt(1+u^2), sin(atan u) = u/sqrt(1+u^2) -- no atan, no second sincos
-    const double u = t / rc.arc;
+    const double u = t * rc.inv_arc;
     const double w1 = 1.0 + u * u;
     const double rs = rsqrt_(w1);
     const cplx e = mk(rs, -rc.omi * (u * rs));
     const cplx taut = t * e;
-    // jacobian (:126-129): e - i*e*omi*t/(arc*(1+u^2)) = e - i*e*omi*u/(1+u^2)
-    const double jd = rc.omi * u / w1;
+    // jacobian (:126-129): e - i*e*omi*t/(arc*(1+u^2)) = e - i*e*omi*u/(1+u^2), 1/(1+u^2) = rs^2
+    const double jd = rc.omi * u * (rs * rs);
     const cplx jacob = e - jd * mul_i(e);
     // lambda = 1 + i*cl*tau~ (:101-106, :131)
     const cplx lambda = mk(1.0 - pc.cl * taut.im, pc.cl * taut.re);
@@ -207,7 +211,6 @@ EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
     const cplx zc = pc.two_over_s * lambda;    // 2/z
     const cplx z4 = z.re < 0 ? z : -z;         // include/functions.h:407
     // nu = qR*deta/(vt*tau~) = (D/vt)/t * conj(e)   (:140)
-    const double it = 1.0 / t;
     const cplx itaut = it * conj(e);           // 1/tau~
     const cplx nu = pc.Dv * itaut;
     const cplx nu2 = nu * nu;
@@ -236,8 +239,7 @@ EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
     if (m >= 1) pw = pw * nu;
     if (m >= 2) pw = pw * nu;
     const cplx f = pw * jacob * se * (i0 * y0 + i1 * y1) * recip(mu);
-    const double ic2 = 1.0 / (c * c);          // include/functions.h:317
-    return ic2 * f;
+    return (ic * ic) * f;                      // f(tan x)/cos^2 x, include/functions.h:317
 }
 
 // Closed-form electron part (src/Parameters.cpp:186-209), m = 1, 2 (m = 0 is zero).

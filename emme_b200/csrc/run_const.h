@@ -16,6 +16,7 @@ inline RunConst make_run_const(const emme_params& p, int npoints, double wr, dou
     rc.qR = p.q * p.R;
     rc.vt = p.vt;
     rc.arc = p.arc_coeff;
+    rc.inv_arc = 1.0 / p.arc_coeff;
     rc.omega_s_i = p.omega_s_i;
     rc.eta_i = p.eta_i;
     rc.wsi_etai = p.omega_s_i * p.eta_i;
