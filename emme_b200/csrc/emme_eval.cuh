@@ -147,8 +147,11 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     const int n0 = (int)(floor(az) + 1.0);
     int n = n0;
     double dn = (double)n0;
-    // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared.
-    const double thr2 = fmax(THRESHOLD * (dn * sqrt(norm2(zc))), THRESHOLD * THRESHOLD);
+    // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared:
+    // max(T*n*|2/z|, T^2).  The first term only wins for |z| < n*1e-7, so |2/z| = 2/|z| is formed
+    // only then.
+    double thr2 = THRESHOLD * THRESHOLD;
+    if (az < 1e-5) thr2 = fmax(THRESHOLD * (dn * (2.0 / az)), thr2);
     // forward recurrence p_{k+1} = p_{k-1} - (2n/z) p_k, two trips per round (no register moves)
     cplx pa = mk(0., 0.), pb = mk(1., 0.);   // pa = p_{k-1}, pb = p_k
     for (;;) {
@@ -156,32 +159,40 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
         pa = cfms(dn * zc, pb, pa);          // pa <- p_{k+1}
         dn += 1.0;
         ++n;
-        if (!le_nonneg(norm2(pa), thr2)) { pb = pa; break; }
+        if (!le_nonneg(norm2(pa), thr2)) break;
         pb = cfms(dn * zc, pa, pb);          // pb <- p_{k+2}
         dn += 1.0;
         ++n;
     }
     cnt.fwd += (unsigned)(n - n0);
-    // the reference starts the backward pass from 1/p_N; the returned ratios y/mu do not depend
-    // on that scale (everything is linear in it), so the complex reciprocal is dropped
-    y0 = mk(1., 0.);
-    y1 = mk(0., 0.);
-    mu = mk(0., 0.);
     --n;
     dn -= 1.0;
     cnt.bwd += (unsigned)n;
-    // 2*(Re z < 0 ? 1 - 2*(n & 1) : 1): alternates with n when Re z < 0
+    // backward recurrence y_{k-1} = (2k/z) y_k + y_{k+1} from y_N = 1 (the reference starts from
+    // 1/p_N; the returned ratios y/mu do not depend on that scale, so the reciprocal is dropped),
+    // mu += 2*(Re z < 0 ? 1 - 2*(k & 1) : 1) * y_k.  Two trips per round: ya/yb swap roles instead
+    // of being moved, and the alternating sign is a pair of constants.
     const bool neg = z.re < 0;
-    double sg = (neg && (n & 1)) ? -2.0 : 2.0;
-    const double flip = neg ? -1.0 : 1.0;
-#pragma unroll 2
-    for (; n > 0; --n) {
-        const cplx yt = cfma(dn * zc, y0, y1);
-        y1 = y0;
-        y0 = yt;
-        mu = mk(fma(sg, y1.re, mu.re), fma(sg, y1.im, mu.im));
-        sg *= flip;
+    const double sgA = (neg && (n & 1)) ? -2.0 : 2.0;   // sign of the first (and every odd) trip
+    const double sgB = neg ? -sgA : sgA;
+    cplx ya = mk(1., 0.), yb = mk(0., 0.);   // ya = y_k ("y0"), yb = y_{k+1} ("y1")
+    mu = mk(0., 0.);
+    for (; n >= 2; n -= 2) {
+        yb = cfma(dn * zc, ya, yb);          // yb <- y_{k-1}; ya is now "y1"
+        mu = mk(fma(sgA, ya.re, mu.re), fma(sgA, ya.im, mu.im));
         dn -= 1.0;
+        ya = cfma(dn * zc, yb, ya);          // ya <- y_{k-2}; yb is now "y1"
+        mu = mk(fma(sgB, yb.re, mu.re), fma(sgB, yb.im, mu.im));
+        dn -= 1.0;
+    }
+    if (n == 1) {
+        yb = cfma(dn * zc, ya, yb);
+        mu = mk(fma(sgA, ya.re, mu.re), fma(sgA, ya.im, mu.im));
+        y0 = yb;
+        y1 = ya;
+    } else {
+        y0 = ya;
+        y1 = yb;
     }
     mu = mu + y0;
 }
