@@ -37,6 +37,8 @@ __constant__ GKTables c_gk31 = EMME_GK31_INIT;
 
 constexpr int STACK_SMEM = 8;    // right-sibling intervals kept in shared memory per lane
 constexpr int BLOCK = 128;
+constexpr int TRIG_DEPTH = 8;                           // node table covers bisection levels 0..8
+constexpr int TRIG_PANELS = (1 << (TRIG_DEPTH + 1)) - 1;   // heap-ordered panels
 #ifndef EMME_ASM_MIN_BLOCKS
 #define EMME_ASM_MIN_BLOCKS 4
 #endif
@@ -95,11 +97,12 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                 unsigned long long n_items_local, unsigned long long shard_index,
                 unsigned long long shard_count, unsigned long long* __restrict__ counter,
                 double2* __restrict__ spill, int spill_cap, unsigned long long* __restrict__ stats,
-                int refill_min) {
+                int refill_min, const double4* __restrict__ trig) {
     constexpr int H = (ORDER - 1) / 2;          // 7 or 15 symmetric node pairs
     const GKTables& T = ORDER == 15 ? c_gk15 : c_gk31;
 
     __shared__ double2 s_stack[STACK_SMEM][BLOCK];   // [slot][thread]: conflict-free
+    __shared__ int s_pid[STACK_SMEM][BLOCK];         // heap index of the stacked panel (-1: untabulated)
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -109,7 +112,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
     const unsigned long long n_pairs = (unsigned long long)rc.N * (rc.N - 1) / 2;
     bool active = false;
     bool warp_exhausted = false;
-    int it_i = 0, it_j = 0, it_m = 0, top = 0;
+    int it_i = 0, it_j = 0, it_m = 0, top = 0, pid = 0;
     PairConst pc;
     cplx sum = mk(0., 0.);
     double abs_tol = 0., l = 0., r = 0.;
@@ -141,6 +144,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                     l = 0.0;
                     r = rc.half_pi;
                     top = 0;
+                    pid = 0;
                     active = true;
                 }
             }
@@ -159,9 +163,21 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
             const int ni = (j + 1) >> 1;                       // node index 0..H
             const double node = (j & 1) ? T.a[ni] : -T.a[ni];  // j = 0: -0*scale + mid = mid
             if (active) {
-                // node position exactly as the reference forms it: scale*x + mid, no FMA
-                const double x = __dadd_rn(__dmul_rn(scale, node), mid);
-                const cplx fx = eval_node(rc, pc, it_m, x, cnt);
+                NodeTrig nt;
+                if (pid >= 0) {
+                    // tabulated panel: tan x, 1/tan x, 1/cos^2 x of this node (built by trig_table_kernel
+                    // with the very same node_trig() and node position arithmetic)
+                    const double2* e = reinterpret_cast<const double2*>(trig + (size_t)pid * (2 * H + 1) + j);
+                    const double2 e0 = __ldg(e), e1 = __ldg(e + 1);
+                    nt.t = e0.x;
+                    nt.it = e0.y;
+                    nt.icsq = e1.x;
+                    nt.x = e1.y;
+                } else {
+                    // node position exactly as the reference forms it: scale*x + mid, no FMA
+                    nt = node_trig(__dadd_rn(__dmul_rn(scale, node), mid));
+                }
+                const cplx fx = eval_node(rc, pc, it_m, nt, cnt);
                 ++n_eval;
                 if (j == 0) {
                     K = mk(T.kw[0] * fx.re, T.kw[0] * fx.im);
@@ -194,15 +210,24 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
             if (split) {
                 // push the right half, continue with the left half (LIFO: left is next)
                 const double2 e = make_double2(mid, r);
-                if (top < STACK_SMEM) s_stack[top][threadIdx.x] = e; else my_spill[top - STACK_SMEM] = e;
+                // children of heap node p are 2p+1 (left) and 2p+2 (right)
+                const int right = (pid >= 0 && 2 * pid + 2 < TRIG_PANELS) ? 2 * pid + 2 : -1;
+                if (top < STACK_SMEM) {
+                    s_stack[top][threadIdx.x] = e;
+                    s_pid[top][threadIdx.x] = right;
+                } else {
+                    my_spill[top - STACK_SMEM] = e;   // deeper than the table: pid is -1 by construction
+                }
                 ++top;
                 max_top = max(max_top, top);
                 r = mid;
+                pid = right >= 0 ? right - 1 : -1;
             } else {
                 sum = sum + integral;
                 if (top > 0) {
                     --top;
                     const double2 e = top < STACK_SMEM ? s_stack[top][threadIdx.x] : my_spill[top - STACK_SMEM];
+                    pid = top < STACK_SMEM ? s_pid[top][threadIdx.x] : -1;
                     l = e.x;
                     r = e.y;
                 } else {
@@ -235,6 +260,42 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
         atomicAdd(&stats[4], n_bwd);
         atomicMax(&stats[5], (unsigned long long)(max_top + 1));
     }
+}
+
+// Node table: one thread per (panel, node) walks from the root panel [0, pi/2] down to its panel
+// with the bisection arithmetic of gauss_kronrod_adaptive (mid = (r+l)/2), forms the node
+// position like the quadrature does and stores node_trig() of it.
+template <int ORDER>
+__global__ void trig_table_kernel(double4* __restrict__ trig, double half_pi) {
+    constexpr int H = (ORDER - 1) / 2;
+    const GKTables& T = ORDER == 15 ? c_gk15 : c_gk31;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= TRIG_PANELS * (2 * H + 1)) return;
+    const int p = e / (2 * H + 1), j = e % (2 * H + 1);
+    int depth = 0;
+    while ((1 << (depth + 1)) - 1 <= p) ++depth;
+    const int idx = p - ((1 << depth) - 1);
+    double l = 0.0, r = half_pi;
+    for (int b = depth - 1; b >= 0; --b) {
+        const double mid = (r + l) / 2;
+        if ((idx >> b) & 1) l = mid; else r = mid;
+    }
+    const double mid = (r + l) / 2, scale = (r - l) / 2;
+    const int ni = (j + 1) >> 1;
+    const double node = (j & 1) ? T.a[ni] : -T.a[ni];
+    const NodeTrig nt = node_trig(__dadd_rn(__dmul_rn(scale, node), mid));
+    trig[e] = make_double4(nt.t, nt.it, nt.icsq, nt.x);
+}
+
+size_t assembly_trig_table_bytes(int order) { return sizeof(double4) * (size_t)TRIG_PANELS * order; }
+
+cudaError_t build_trig_table(int order, void* trig, double half_pi, cudaStream_t stream) {
+    const int n = TRIG_PANELS * order;
+    if (order == 15)
+        trig_table_kernel<15><<<(n + 127) / 128, 128, 0, stream>>>((double4*)trig, half_pi);
+    else
+        trig_table_kernel<31><<<(n + 127) / 128, 128, 0, stream>>>((double4*)trig, half_pi);
+    return cudaGetLastError();
 }
 
 // Diagonal entries (include/solver.h:443 and :465-470).
@@ -276,7 +337,7 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
                             const double* bi, void* A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches, int refill_min) {
+                            unsigned long long* n_launches, int refill_min, const void* trig) {
     const unsigned long long N = rc.N;
     const unsigned long long n_items = N * (N - 1) / 2 * (rc.em ? 3ULL : 1ULL);
     const unsigned long long sc = shard_count, si = shard_index;
@@ -302,11 +363,11 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
         if (rc.order == 15) {
             assemble_kernel<15><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats, refill_min);
+                stats, refill_min, (const double4*)trig);
         } else {
             assemble_kernel<31><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats, refill_min);
+                stats, refill_min, (const double4*)trig);
         }
     }
     return cudaGetLastError();

@@ -18,5 +18,9 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
                             const double* bi, void* A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches, int refill_min);
+                            unsigned long long* n_launches, int refill_min, const void* trig);
+
+// per-order table of node_trig() for the first bisection levels (built once per handle)
+size_t assembly_trig_table_bytes(int order);
+cudaError_t build_trig_table(int order, void* trig, double half_pi, cudaStream_t stream);
 }  // namespace emme

@@ -47,6 +47,7 @@ struct emme_solver {
     void *A = nullptr, *Aold = nullptr, *Ad = nullptr, *W = nullptr;
     unsigned long long *d_counter = nullptr, *d_stats = nullptr;
     void* d_spill = nullptr;
+    void* d_trig = nullptr;           // node table of kernel 1
     int spill_cap = 0, grid_blocks = 0;
     void* d_dense_ws = nullptr;
     double2* d_trace = nullptr;
@@ -132,6 +133,7 @@ int emme_destroy(emme_solver* s) {
     cudaFree(s->d_counter);
     cudaFree(s->d_stats);
     cudaFree(s->d_spill);
+    cudaFree(s->d_trig);
     cudaFree(s->d_dense_ws);
     cudaFree(s->d_trace);
     cudaFree(s->d_info);
@@ -190,6 +192,9 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
                               emme::assembly_groups_per_block(p->integration_start_points);
         CU(cudaMalloc(&s->d_spill, groups * s->spill_cap * sizeof(double2)));
     }
+    CU(cudaMalloc(&s->d_trig, emme::assembly_trig_table_bytes(p->integration_start_points)));
+    CU(emme::build_trig_table(p->integration_start_points, s->d_trig, M_PI / 2.0, s->stream));
+    ++s->launches;
     CU(cudaMalloc(&s->d_trace, sizeof(double2)));
     CU(cudaMalloc(&s->d_info, sizeof(int)));
     CU(cudaMalloc(&s->d_flag, sizeof(int)));
@@ -213,7 +218,7 @@ static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, in
     CU(cudaEventRecord(s->ev0, s->stream));
     CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, dst, shard_index, shard_count,
                              s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->grid_blocks,
-                             s->stream, &s->launches, s->refill_min));
+                             s->stream, &s->launches, s->refill_min, s->d_trig));
     CU(cudaEventRecord(s->ev1, s->stream));
     return 0;
 }

@@ -197,14 +197,30 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     mu = mu + y0;
 }
 
-// g(x) for mode m (0, 1, 2).  x in (0, pi/2).
-EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
-                       EvalCounters& cnt) {
-    // t = tan x, 1/t and 1/cos^2 x from one sincos and two reciprocals (include/functions.h:316-317)
+// What the integrand needs of a quadrature node x in (0, pi/2): t = tan x, 1/t and 1/cos^2 x
+// (the [0,inf) -> [0,pi/2] map of include/functions.h:315-318).  It depends on the panel and the
+// node only, not on the integrand, so the kernel tabulates it for the first levels of the
+// bisection tree (node_trig is the single definition both the table and the direct path use).
+struct NodeTrig {
+    double t, it, icsq, x;
+};
+
+EMME_HD NodeTrig node_trig(double x) {
     double sx, c;
     sincos(x, &sx, &c);
-    const double ic = 1.0 / c, it = c / sx;
-    const double t = sx * ic;
+    const double ic = 1.0 / c;
+    NodeTrig n;
+    n.t = sx * ic;
+    n.it = c / sx;
+    n.icsq = ic * ic;
+    n.x = x;
+    return n;
+}
+
+// g(x) for mode m (0, 1, 2) at the node described by nt.
+EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, const NodeTrig& nt,
+                       EvalCounters& cnt) {
+    const double t = nt.t, it = nt.it;
     // contour rotation e = exp(-i*omi*atan(u)), u = t/arc, tau~ = t*e (src/Parameters.cpp:121-124):
     // cos(atan u) = 1/sqrt(1+u^2), sin(atan u) = u/sqrt(1+u^2) -- no atan, no second sincos
     const double u = t * rc.inv_arc;
@@ -250,7 +266,7 @@ EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, double x,
     if (m >= 1) pw = pw * nu;
     if (m >= 2) pw = pw * nu;
     const cplx f = pw * jacob * se * (i0 * y0 + i1 * y1) * recip(mu);
-    return (ic * ic) * f;                      // f(tan x)/cos^2 x, include/functions.h:317
+    return nt.icsq * f;                        // f(tan x)/cos^2 x, include/functions.h:317
 }
 
 // Closed-form electron part (src/Parameters.cpp:186-209), m = 1, 2 (m = 0 is zero).
