@@ -130,3 +130,46 @@ def test_deep_stack_spills_to_global(native_lib):
     c = parity.compare(A, ref)
     assert c["max_abs_over_max"] < 1e-13
     assert st["max_stack"] >= 8
+
+
+def _variant(case, **subs):
+    txt = cases.input_path(case).read_text()
+    for old, new in subs.values():
+        assert old in txt, old
+        txt = txt.replace(old, new)
+    return Input(text=txt)
+
+
+@pytest.mark.parametrize("label,inp_args,omega", [
+    ("n2", dict(n=('"npoints": 32', '"npoints": 2')), -0.8 + 0.25j),
+    ("n3", dict(n=('"npoints": 32', '"npoints": 3')), -0.8 + 0.25j),
+    ("n33_ragged", dict(n=('"npoints": 32', '"npoints": 33')), -0.8 + 0.25j),
+    ("n17_em", dict(n=('"npoints": 32', '"npoints": 17'), b=('"beta_e": 0.00', '"beta_e": 0.01')), 0.4 + 0.2j),
+    ("re_omega_zero", dict(), 0.0 + 0.3j),
+    ("prec_zero", dict(p=('"integration_accuracy": 1.0e-6', '"integration_accuracy": 0.0')), -0.8 + 0.25j),
+    ("maxdepth_2", dict(d=('"integration_iteration_limit": 100', '"integration_iteration_limit": 2')), -0.8 + 0.25j),
+    ("maxdepth_0", dict(d=('"integration_iteration_limit": 100', '"integration_iteration_limit": 0')), -0.8 + 0.25j),
+    ("gk31_loose", dict(o=('"integration_start_points": 15', '"integration_start_points": 31'),
+                        t=('"integration_precision": 1.0e-6', '"integration_precision": 1.0e-2')), -0.8 + 0.25j),
+])
+def test_edge_cases_against_oracle(label, inp_args, omega, native_lib):
+    """Smallest and ragged grids, Re(omega) = 0, zero absolute accuracy, depth limits 0 and 2: the CUDA
+    path and the oracle must take the same adaptive decisions and agree to rounding."""
+    import oracle_lib as O
+    inp = _variant("c1_n32", **inp_args)
+    p, n = inp.params()
+    eta, g, bi = inp.tables()
+    s = EigenSolver.from_input(inp)
+    A = s.matrixAssembler(omega)
+    ref, ost = O.assemble(cases.oracle_params(p), eta, g, bi, p.dx, omega)
+    c = parity.assert_parity(A, ref, em=p.beta_e != 0, label=label)
+    report(label, c)
+    assert s.stats()["evals"] == ost["evals"], (s.stats(), ost)
+
+
+def test_bad_quadrature_order_is_rejected(native_lib):
+    from emme_b200 import EmmeError, capi
+    inp = _variant("c1_n32", o=('"integration_start_points": 15', '"integration_start_points": 21'))
+    with pytest.raises(EmmeError, match="integration_start_points should be 15 or 31") as ei:
+        EigenSolver.from_input(inp)
+    assert ei.value.code == capi.E_BAD_ORDER

@@ -136,3 +136,43 @@ def test_pivoting_fallback_is_taken_and_correct(native_lib):
     d = s.trace_delta(D, B)
     assert abs(d + 1.0 / np.trace(np.linalg.solve(D, B))) <= 1e-12 * abs(d)
     assert s.stats()["pivot_fallbacks"] == 1          # diagonally dominant: no fallback
+
+
+def test_host_program_scan_matches_reference_program(tmp_path, native_lib):
+    """A 4-point two-sided scan through the C++ `emme` program against output.json of the UNMODIFIED
+    reference program (tests/golden/scan_c1_n32.json: continuation of omega between points, the
+    turning point, eigenMatrics file names; the reference prints 6 significant digits)."""
+    import json
+    import re
+    import subprocess
+    from emme_b200 import build
+    build.build_all()
+    gold = json.loads((cases.GOLD / "scan_c1_n32.json").read_text())
+    (tmp_path / "input.json").write_text(cases.input_path("c1_scan_n32").read_text())
+    (tmp_path / "eigenMatrics").mkdir()
+    r = subprocess.run([str(build.EXE)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    out = (tmp_path / "output.json").read_text()
+    vals = [float(v) for v in re.findall(r'"scan_value": ([-0-9.e+]+)', out)]
+    evs = [(float(a), float(b)) for a, b in re.findall(r'"eigenvalue": \[\s*([-0-9.e+]+),\s*([-0-9.e+]+)', out)]
+    assert vals == gold["scan_values"]
+    assert len(evs) == len(gold["eigenvalues"])
+    for (a, b), (ra, rb) in zip(evs, gold["eigenvalues"]):
+        assert abs(a - ra) <= 2e-6 * max(1, abs(ra)) and abs(b - rb) <= 2e-6 * max(1, abs(rb)), (evs, gold)
+    assert sorted(p.name for p in (tmp_path / "eigenMatrics").iterdir()) == gold["files"]
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_trace_delta_tiny(dim, native_lib):
+    rng = np.random.default_rng(100 + dim)
+    A = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim)) + 3 * np.eye(dim)
+    B = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    inp = Input(cases.input_path("c1_n32"))
+    p, _ = inp.params()
+    n = max(dim, 2)
+    s = EigenSolver(p, n, np.linspace(-1, 1, n), np.zeros(n), np.ones(n))
+    if dim == 1:
+        pytest.skip("npoints >= 2 is the smallest mesh (Grid divides by npoints-1)")
+    d = s.trace_delta(A, B)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    assert abs(d - ref) <= 1e-12 * abs(ref)
