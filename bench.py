@@ -307,6 +307,13 @@ def bench_b200(args, rank, local_rank, world):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        tr = json.loads((ROOT / "profiles" / "traffic.json").read_text())["assemble_kernel"].get(str(npoints))
+        if tr:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
 
     extra = {}
     if rank == 0 and not args.quick:
@@ -384,7 +391,8 @@ def bench_b200(args, rank, local_rank, world):
                          "flops_per_launch": run["flops"] / args.steps,
                          "avg_launch_ms": run["asm_ms"] / args.steps,
                          "hbm_achieved_gbs": 16.0 * dim * dim / (run["asm_ms"] / args.steps * 1e-3) / 1e9,
-                         "hbm_peak_gbs": hbm_peak, "traffic": None,
+                         "hbm_peak_gbs": hbm_peak, "traffic": traffic,
+                         "algorithmic_bytes": 16 * dim * dim,
                          "evals": st["evals"], "fwd_trips": st["fwd_trips"], "bwd_trips": st["bwd_trips"]},
             "roofline_dense": {"kernel": "LU + triangular solves (kernel 2)", "bound": "fp64",
                                "achieved": dense_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
