@@ -61,6 +61,9 @@ struct emme_solver {
     int refill_min = 16;
     int optimistic = 1;               // try the interchange-free factorisation first
     int null_optimistic = 1;
+    int use_graph = 1;                // replay the optimistic dense step as a CUDA graph
+    cudaGraphExec_t dense_graph = nullptr;
+    unsigned long long dense_graph_launches = 0;
     unsigned long long pivot_fallbacks = 0;
     int* d_flag = nullptr;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
@@ -138,6 +141,7 @@ int emme_destroy(emme_solver* s) {
     cudaFree(s->d_trace);
     cudaFree(s->d_info);
     cudaFree(s->d_flag);
+    if (s->dense_graph) cudaGraphExecDestroy(s->dense_graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -200,11 +204,13 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     CU(cudaMalloc(&s->d_flag, sizeof(int)));
     if (const char* e = std::getenv("EMME_DENSE_OPTIMISTIC")) s->optimistic = std::atoi(e) != 0;
     if (const char* e = std::getenv("EMME_DENSE_TAU")) emme::dense_set_pivot_threshold(std::atof(e));
+    if (const char* e = std::getenv("EMME_DENSE_GRAPH")) s->use_graph = std::atoi(e) != 0;
     *out = s.release();
     return 0;
 }
 
 static int ensure_newton_buffers(emme_solver* s) {
+    CU(emme::dense_prepare());
     if (!s->Aold) CU(cudaMalloc(&s->Aold, s->bytes()));
     if (!s->Ad) CU(cudaMalloc(&s->Ad, s->bytes()));
     if (!s->W) CU(cudaMalloc(&s->W, s->bytes()));
@@ -283,8 +289,39 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
             ++s->pivot_fallbacks;
         }
         CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
-        CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
-                                    s->stream, &s->launches, optimistic, s->d_flag));
+        if (optimistic && s->use_graph) {
+            // The interchange-free path is a fixed sequence of ~5*dim/32 short launches on fixed
+            // buffers: captured once into a CUDA graph and replayed (the launch-bound inner loop).
+            if (!s->dense_graph) {
+                cudaGraph_t g = nullptr;
+                unsigned long long nl = 0;
+                CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+                cudaError_t le = emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace,
+                                                          s->d_info, s->stream, &nl, 1, s->d_flag);
+                cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+                if (le != cudaSuccess || ce != cudaSuccess || !g) {
+                    cudaGetLastError();
+                    s->use_graph = 0;          // capture not possible: fall back to plain launches
+                    if (g) cudaGraphDestroy(g);
+                } else {
+                    cudaError_t ie = cudaGraphInstantiate(&s->dense_graph, g, 0);
+                    cudaGraphDestroy(g);
+                    if (ie != cudaSuccess) {
+                        cudaGetLastError();
+                        s->dense_graph = nullptr;
+                        s->use_graph = 0;
+                    }
+                    s->dense_graph_launches = nl;
+                }
+            }
+        }
+        if (optimistic && s->use_graph && s->dense_graph) {
+            CU(cudaGraphLaunch(s->dense_graph, s->stream));
+            s->launches += s->dense_graph_launches;
+        } else {
+            CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
+                                        s->stream, &s->launches, optimistic, s->d_flag));
+        }
         CU(cudaEventRecord(e1, s->stream));
         CU(cudaMemcpyAsync(tr, s->d_trace, sizeof tr, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));

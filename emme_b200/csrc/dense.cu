@@ -808,6 +808,8 @@ size_t dense_workspace_bytes(int dim) {
     return sizeof(PanelCand) * 2 * (size_t)nblk + sizeof(int) * (size_t)dim + 64;
 }
 
+cudaError_t dense_prepare() { return gemm_setup(); }   // one-time function attributes (before any capture)
+
 static int g_nbo = 0;     // outer block width (multiple of NB); 0 = choose by size
 void dense_set_outer_block(int nbo) {
     g_nbo = nbo <= 0 ? 0 : (nbo < NB ? NB : (nbo / NB) * NB);

@@ -26,6 +26,7 @@ void dense_set_pivot_threshold(double tau);
 // Ad = (A - Aold)/delta over n complex entries
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,
                           double di, int sms, cudaStream_t stream);
+cudaError_t dense_prepare();
 void dense_force_grid_panel(bool on);
 void dense_set_outer_block(int nbo);
 // measured DFMA throughput (TFLOP/s) of the current device
