@@ -337,7 +337,8 @@ def bench_b200(args, rank, local_rank, world):
     if world > 1 and args.mode_rows:
         inp_r = Input(text=c1_text(npoints))
         pr, nr = inp_r.params()
-        ss = parallel.ShardedEigenSolver(pr, nr, *inp_r.tables(), device=local_rank)
+        ss = parallel.ShardedEigenSolver(pr, nr, *inp_r.tables(), device=local_rank,
+                                         exchange=args.exchange)
         ss.seed(omega0 * 1.01)
         for _ in range(2):
             ss.newtonTraceSecantIteration()
@@ -352,7 +353,9 @@ def bench_b200(args, rank, local_rank, world):
         rs = max_over_ranks(t1 - t0)
         row_sharded = {"scaling": "strong", "value": dim * dim * args.steps / rs, "unit": "elements/s",
                        "ms_per_step": 1e3 * rs / args.steps, "omega": [ss.eigen_value.real, ss.eigen_value.imag],
-                       "collective": "NCCL all-reduce(sum) of disjoint shares, 16*dim^2 bytes per assembly"}
+                       "exchange": ("peer stores from inside the assembly kernel (CUDA IPC over NVLink) + barrier"
+                                    if args.exchange == "p2p" else
+                                    "NCCL all-reduce(sum) of disjoint shares, 16*dim^2 bytes per assembly")}
         ss.close()
 
     cpu_baseline = None
@@ -420,6 +423,8 @@ def main():
     ap.add_argument("--npoints", type=int, default=8192)
     ap.add_argument("--mode", default="scan", choices=["scan", "rows"])
     ap.add_argument("--quick", action="store_true", help="skip the cpu_baseline and C1 extras")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allreduce"],
+                    help="row-sharded mode: fused peer stores or NCCL all-reduce")
     args = ap.parse_args()
     args.mode_rows = True
     rank = int(os.environ.get("RANK", "0"))

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "emme_step_begin": (C.c_int, [_vp]),
     "emme_step_finish": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "emme_matrix_device_ptr": (_vp, [_vp, C.c_int]),
+    "emme_ipc_export": (C.c_int, [_vp, C.c_int, _vp]),
+    "emme_ipc_import": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "emme_copy_matrix": (C.c_int, [_vp, C.c_int, _vp]),
     "emme_null_space": (C.c_int, [_vp, _vp]),
     "emme_get_stats": (C.c_int, [_vp, C.POINTER(EmmeStats)]),

@@ -61,12 +61,18 @@ __device__ __forceinline__ void decode_pair(unsigned long long p, int N, int& i,
     j = i + (int)d;
 }
 
-__device__ __forceinline__ void store_c(double2* A, size_t idx, cplx v) {
-    A[idx] = make_double2(v.re, v.im);
+// Destination(s) of the assembled entries: the local matrix, or -- pair-sharded multi-GPU
+// assembly -- the same matrix on every GPU of the node (peer pointers mapped over NVLink): each
+// rank stores its entries straight into all peers while it computes, so no collective follows.
+__device__ __forceinline__ void store_c(const PeerSet& dst, size_t idx, cplx v) {
+    const double2 e = make_double2(v.re, v.im);
+#pragma unroll
+    for (int r = 0; r < EMME_MAX_PEERS; ++r)
+        if (r < dst.n) dst.p[r][idx] = e;
 }
 
 // Write the entries produced by item (i, j, m) -- include/solver.h:448-453 and :476-504.
-__device__ __forceinline__ void scatter(const RunConst& rc, double2* A, int i, int j, int m,
+__device__ __forceinline__ void scatter(const RunConst& rc, const PeerSet& A, int i, int j, int m,
                                         cplx kappa_all) {
     const int N = rc.N;
     const size_t dim = rc.em ? 2 * (size_t)N : (size_t)N;
@@ -93,7 +99,7 @@ __device__ __forceinline__ void scatter(const RunConst& rc, double2* A, int i, i
 template <int ORDER>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double* __restrict__ gt,
-                const double* __restrict__ bt, double2* __restrict__ A,
+                const double* __restrict__ bt, const PeerSet A,
                 unsigned long long n_items_local, unsigned long long shard_index,
                 unsigned long long shard_count, unsigned long long* __restrict__ counter,
                 double2* __restrict__ spill, int spill_cap, unsigned long long* __restrict__ stats,
@@ -299,17 +305,16 @@ cudaError_t build_trig_table(int order, void* trig, double half_pi, cudaStream_t
 }
 
 // Diagonal entries (include/solver.h:443 and :465-470).
-__global__ void diagonal_kernel(const RunConst rc, const double* __restrict__ bt,
-                                double2* __restrict__ A) {
+__global__ void diagonal_kernel(const RunConst rc, const double* __restrict__ bt, const PeerSet A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rc.N) return;
     const size_t N = rc.N;
     const size_t dim = rc.em ? 2 * N : N;
-    A[(size_t)i * dim + i] = make_double2(rc.diag_es, 0.);
+    store_c(A, (size_t)i * dim + i, mk(rc.diag_es, 0.));
     if (rc.em) {
-        A[(size_t)i * dim + (i + N)] = make_double2(0., 0.);
-        A[(size_t)(i + N) * dim + i] = make_double2(0., 0.);
-        A[(size_t)(i + N) * dim + (i + N)] = make_double2(rc.diag_em * bt[i], 0.);
+        store_c(A, (size_t)i * dim + (i + N), mk(0., 0.));
+        store_c(A, (size_t)(i + N) * dim + i, mk(0., 0.));
+        store_c(A, (size_t)(i + N) * dim + (i + N), mk(rc.diag_em * bt[i], 0.));
     }
 }
 
@@ -334,7 +339,7 @@ int assembly_groups_per_block(int order) { (void)order; return BLOCK; }  // stac
 int assembly_stack_smem() { return STACK_SMEM; }
 
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
-                            const double* bi, void* A, int shard_index, int shard_count,
+                            const double* bi, const PeerSet& A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
                             unsigned long long* n_launches, int refill_min, const void* trig) {
@@ -355,18 +360,18 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
     e = cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     if (shard_index == 0) {
-        diagonal_kernel<<<(rc.N + 127) / 128, 128, 0, stream>>>(rc, bi, (double2*)A);
+        diagonal_kernel<<<(rc.N + 127) / 128, 128, 0, stream>>>(rc, bi, A);
         if (n_launches) ++*n_launches;
     }
     if (n_local > 0) {
         if (n_launches) ++*n_launches;
         if (rc.order == 15) {
             assemble_kernel<15><<<grid_blocks, BLOCK, 0, stream>>>(
-                rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,
+                rc, eta, g, bi, A, n_local, si, sc, counter, (double2*)spill, spill_cap,
                 stats, refill_min, (const double4*)trig);
         } else {
             assemble_kernel<31><<<grid_blocks, BLOCK, 0, stream>>>(
-                rc, eta, g, bi, (double2*)A, n_local, si, sc, counter, (double2*)spill, spill_cap,
+                rc, eta, g, bi, A, n_local, si, sc, counter, (double2*)spill, spill_cap,
                 stats, refill_min, (const double4*)trig);
         }
     }

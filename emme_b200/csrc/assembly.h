@@ -2,8 +2,16 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#define EMME_MAX_PEERS 8
+
 namespace emme {
 struct RunConst;
+
+// where kernel 1 stores its entries: p[0..n) are the same dim x dim matrix on n GPUs
+struct PeerSet {
+    double2* p[EMME_MAX_PEERS];
+    int n;
+};
 
 // persistent grid size (SM count x resident CTAs) for the given Gauss-Kronrod order
 int assembly_grid_blocks(int order, int device);
@@ -15,7 +23,7 @@ int assembly_stack_smem();
 // spill_cap == 0) are device scratch owned by the handle.  refill_min: idle lanes of a warp
 // refill together once at least this many are idle (1 = per lane, 32 = whole-warp batches).
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
-                            const double* bi, void* A, int shard_index, int shard_count,
+                            const double* bi, const PeerSet& A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
                             unsigned long long* n_launches, int refill_min, const void* trig);

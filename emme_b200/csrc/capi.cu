@@ -56,6 +56,11 @@ struct emme_solver {
     bool seeded = false;
     zc w{0, 0}, dw{0, 0};
     int shard_index = 0, shard_count = 1;
+    // pair-sharded assembly with direct peer stores: the two physical matrix buffers that A and
+    // A_old alternate between, and the same two buffers of every peer (CUDA IPC mappings)
+    void* phys[2] = {nullptr, nullptr};
+    void* peer_phys[2][EMME_MAX_PEERS] = {};
+    int peer_count = 0;               // 0: local stores only
     emme_stats stats{};
     unsigned long long launches = 0;
     int refill_min = 16;
@@ -126,6 +131,9 @@ int emme_set_params(emme_solver* s, const emme_params* p) {
 int emme_destroy(emme_solver* s) {
     if (!s) return 0;
     cudaSetDevice(s->device);
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < EMME_MAX_PEERS; ++r)
+            if (s->peer_phys[w][r] && s->peer_phys[w][r] != s->phys[w]) cudaIpcCloseMemHandle(s->peer_phys[w][r]);
     cudaFree(s->d_eta);
     cudaFree(s->d_g);
     cudaFree(s->d_bi);
@@ -221,8 +229,16 @@ static int ensure_newton_buffers(emme_solver* s) {
 // enqueue one assembly of A(w) into `dst` (device), this handle's shard only
 static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, int shard_count) {
     RunConst rc = emme::make_run_const(s->p, s->N, w.real(), w.imag());
+    emme::PeerSet ps{};
+    ps.n = 1;
+    ps.p[0] = (double2*)dst;
+    if (s->peer_count > 1 && (dst == s->phys[0] || dst == s->phys[1])) {
+        const int which = dst == s->phys[0] ? 0 : 1;
+        ps.n = s->peer_count;
+        for (int r = 0; r < s->peer_count; ++r) ps.p[r] = (double2*)s->peer_phys[which][r];
+    }
     CU(cudaEventRecord(s->ev0, s->stream));
-    CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, dst, shard_index, shard_count,
+    CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, ps, shard_index, shard_count,
                              s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->grid_blocks,
                              s->stream, &s->launches, s->refill_min, s->d_trig));
     CU(cudaEventRecord(s->ev1, s->stream));
@@ -368,10 +384,54 @@ int emme_shard_config(emme_solver* s, int shard_index, int shard_count) {
 // When sharded, the caller completes the matrix between begin/middle/finish; the buffer is
 // zeroed first so that shares can be summed.
 static int assemble_current(emme_solver* s) {
-    if (s->shard_count > 1) CU(cudaMemsetAsync(s->A, 0, s->bytes(), s->stream));
+    // with peer stores every rank writes every entry of every GPU's matrix: nothing to zero or sum
+    if (s->shard_count > 1 && s->peer_count <= 1) CU(cudaMemsetAsync(s->A, 0, s->bytes(), s->stream));
     int rc = enqueue_assembly(s, s->w, s->A, s->shard_index, s->shard_count);
     if (rc) return rc;
     return collect_stats(s);
+}
+
+// ---- peer-store plumbing (CUDA IPC): see emme_b200/parallel.py::ShardedEigenSolver ----
+int emme_ipc_export(emme_solver* s, int which, void* handle64) {
+    if (!s) return fail(-1, "null handle");
+    if (which < 0 || which > 1) return fail(-2, "emme_ipc_export: which must be 0 or 1");
+    if (!handle64) return fail(-3, "null output");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_newton_buffers(s);
+    if (rc) return rc;
+    if (!s->phys[0]) {
+        s->phys[0] = s->A;
+        s->phys[1] = s->Aold;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->phys[which]));
+    std::memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int emme_ipc_import(emme_solver* s, int peer_rank, int peer_count, int which, const void* handle64) {
+    if (!s) return fail(-1, "null handle");
+    if (peer_count < 1 || peer_count > EMME_MAX_PEERS) return fail(-3, "emme_ipc_import: 1..8 peers");
+    if (peer_rank < 0 || peer_rank >= peer_count) return fail(-2, "emme_ipc_import: bad peer rank");
+    if (which < 0 || which > 1) return fail(-4, "emme_ipc_import: which must be 0 or 1");
+    CU(cudaSetDevice(s->device));
+    if (!s->phys[0]) return fail(EMME_E_STATE, "emme_ipc_import before emme_ipc_export");
+    if (peer_rank == s->shard_index) {
+        s->peer_phys[which][peer_rank] = s->phys[which];
+    } else {
+        if (!handle64) return fail(-5, "null handle bytes");
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_phys[which][peer_rank] = ptr;
+    }
+    bool all = true;
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < peer_count; ++r) all = all && s->peer_phys[w][r] != nullptr;
+    if (all) s->peer_count = peer_count;   // switch on once every mapping is present
+    return 0;
 }
 
 int emme_seed_begin(emme_solver* s, double w0r, double w0i) {

@@ -7,11 +7,14 @@ Two ways the path shards:
   starts are dealt round-robin to ranks; only (omega, iterations, status) is gathered at the end.
   `scan_partition`, `gather_results`.
 * row/pair-sharded assembly (strong scaling): the work items of ONE assembly (pairs i<j in
-  diagonal-major order, times 3 modes when electromagnetic) are dealt round-robin to ranks
-  (`shard_items`); each rank fills its entries of a zeroed dim x dim buffer and one all-reduce
-  (sum) over NVLink completes the matrix on every rank -- the shares are disjoint, so the sum is
-  bit-identical to a single-GPU assembly; the dense step is then replicated on every rank
-  (identical inputs give identical delta, no broadcast needed).  `ShardedEigenSolver`.
+  diagonal-major order, times 3 modes when electromagnetic) are dealt to ranks in chunks of 32
+  (`shard_items`).  Default (`exchange="p2p"`): the ranks map each other's matrices with CUDA IPC
+  and the assembly kernel stores every entry it computes straight into the matrix of EVERY GPU
+  over NVLink while it computes -- compute and exchange are one kernel, only a barrier follows.
+  Fallback (`exchange="allreduce"`): each rank fills its entries of a zeroed buffer and one NCCL
+  all-reduce (sum) completes the matrix; the shares are disjoint, so either way the result is
+  bit-identical to a single-GPU assembly.  The dense step is replicated on every rank (identical
+  inputs give identical delta, no broadcast needed).  `ShardedEigenSolver`.
 """
 import ctypes as C
 
@@ -21,10 +24,17 @@ from . import capi
 from .solver import EigenSolver
 
 
-def shard_items(n_items, rank, world):
-    """Number of work items rank `rank` owns under the kernel's round-robin rule
-    (global item = k*world + rank, emme_b200/csrc/assembly.cu)."""
-    return (n_items - rank + world - 1) // world if n_items > rank else 0
+def shard_items(n_items, rank, world, chunk=32):
+    """Number of work items rank `rank` owns: chunks of `chunk` consecutive items are dealt
+    round-robin (launch_assembly in emme_b200/csrc/assembly.cu uses chunk = 32, one warp cohort)."""
+    n_chunks = (n_items + chunk - 1) // chunk
+    if n_chunks <= rank:
+        return 0
+    mine = (n_chunks - rank + world - 1) // world
+    n = mine * chunk
+    if (mine - 1) * world + rank == n_chunks - 1:      # I own the (possibly partial) last chunk
+        n -= n_chunks * chunk - n_items
+    return n
 
 
 def n_work_items(npoints, electromagnetic):
@@ -70,7 +80,7 @@ class ShardedEigenSolver(EigenSolver):
     Same public surface (seed, newtonTraceSecantIteration, eigen_value ...); every rank ends each
     call with the full matrices and the same eigen_value."""
 
-    def __init__(self, params, npoints, eta, g, bi, device=0, group=None):
+    def __init__(self, params, npoints, eta, g, bi, device=0, group=None, exchange="p2p"):
         import torch.distributed as dist
         super().__init__(params, npoints, eta, g, bi, device=device)
         self._group = group
@@ -78,14 +88,35 @@ class ShardedEigenSolver(EigenSolver):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.shard_config(self.rank, self.world)
+        self.exchange = exchange if self.world > 1 else "none"
+        if self.exchange == "p2p":
+            self._map_peers()
+
+    def _map_peers(self):
+        """Exchange CUDA IPC handles of the two matrix buffers; every rank maps every peer."""
+        import torch.distributed as dist
+        mine = []
+        for which in (0, 1):
+            buf = C.create_string_buffer(64)
+            capi.check(self._lib.emme_ipc_export(self._h, which, buf))
+            mine.append(buf.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self._group)
+        for r, handles in enumerate(everyone):
+            for which in (0, 1):
+                capi.check(self._lib.emme_ipc_import(self._h, r, self.world, which,
+                                                     C.create_string_buffer(handles[which], 64)))
 
     def _complete(self):
-        """Sum the ranks' disjoint shares of eigen_matrix (all-reduce over NVLink)."""
+        """Make eigen_matrix complete on every rank."""
         import torch
         import torch.distributed as dist
         if self.world == 1:
             return
-        self.synchronize()                       # shard kernel finished on the handle's stream
+        self.synchronize()                       # my kernel (and its peer stores) has finished
+        if self.exchange == "p2p":
+            dist.barrier(group=self._group)      # ... and so has everyone else's
+            return
         t = device_view(self, 0, self._device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group)
         torch.cuda.current_stream().synchronize()

@@ -126,6 +126,13 @@ int emme_seed_finish(emme_solver* s);                          /* A' = (A-A_old)
 int emme_step_begin(emme_solver* s);                           /* dense step, omega+=delta, assemble shard */
 int emme_step_finish(emme_solver* s, double* wr, double* wi, double* dr, double* di);
 void* emme_matrix_device_ptr(emme_solver* s, int which);
+/* Fused exchange (no collective): export the CUDA IPC handles (64 bytes each) of the two physical
+ * buffers eigen_matrix / eigen_matrix_old alternate between, import every peer's handles, and
+ * from then on the assembly kernel stores each entry it computes straight into the matrix of
+ * EVERY GPU over NVLink.  The caller only needs a barrier after begin/middle (all ranks done
+ * writing) before finish.  Up to 8 peers (one NVSwitch box). */
+int emme_ipc_export(emme_solver* s, int which, void* handle64);
+int emme_ipc_import(emme_solver* s, int peer_rank, int peer_count, int which, const void* handle64);
 
 /* EigenSolver::nullSpace (include/solver.h:58-112): the eigenvector, i.e. the right singular
  * vector of eigen_matrix for its smallest singular value (dim complex128 to host_out), by

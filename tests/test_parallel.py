@@ -19,11 +19,15 @@ def test_shard_items_partition_is_exact():
         for world in (1, 2, 3, 4, 8):
             parts = [parallel.shard_items(total, r, world) for r in range(world)]
             assert sum(parts) == total
-            assert max(parts) - min(parts) <= 1
-            # the kernel's rule: global item = k*world + rank < total for k < parts[rank]
+            assert max(parts) - min(parts) <= 32
+            # the kernel's rule: local item k -> global (k//32)*32*world + rank*32 + k%32, all < total
+            seen = set()
             for r in range(world):
-                if parts[r]:
-                    assert (parts[r] - 1) * world + r < total <= parts[r] * world + r + world - 1 + 1
+                for k in range(parts[r]):
+                    gk = (k // 32) * 32 * world + r * 32 + k % 32
+                    assert gk < total
+                    seen.add(gk)
+            assert len(seen) == total
 
 
 def test_scan_partition_round_robin():
@@ -61,7 +65,8 @@ def _worker(rank, world, port, out):
         full = np.arange(1, total + 1, dtype=np.float64) * 1.25
         share = np.zeros(total)
         for k in range(parallel.shard_items(total, rank, world)):
-            share[k * world + rank] = full[k * world + rank]
+            gk = (k // 32) * 32 * world + rank * 32 + k % 32
+            share[gk] = full[gk]
         t = torch.from_numpy(share)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ok = bool(np.array_equal(t.numpy(), full))
