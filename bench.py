@@ -333,6 +333,24 @@ def bench_b200(args, rank, local_rank, world):
                        "reference_omega": [-0.8234840422998696, 0.25848499305912503]}
         s1.close()
 
+    if rank == 0 and world == 1 and not args.quick:
+        # BASELINE configs[3]: the grid-size sweep, one seed + two iterates per size
+        sweep = []
+        for nn in (512, 1024, 2048, 4096):
+            si = Input(text=c1_text(nn))
+            sv = EigenSolver.from_input(si, device=local_rank)
+            sv.seed(omega0)
+            sv.newtonTraceSecantIteration()
+            sv.newtonTraceSecantIteration()
+            ss_ = sv.stats()
+            fl = algorithmic_flops(ss_)
+            sweep.append({"npoints": nn, "assemble_ms": ss_["assemble_ms"], "dense_ms": ss_["dense_ms"],
+                          "elements_per_s": nn * nn / ((ss_["assemble_ms"] + ss_["dense_ms"]) * 1e-3),
+                          "assemble_tflops": fl / (ss_["assemble_ms"] * 1e-3) / 1e12,
+                          "assemble_frac_of_fp64_peak": fl / (ss_["assemble_ms"] * 1e-3) / 1e12 / peak_tf.value})
+            sv.close()
+        extra["sweep"] = sweep
+
     row_sharded = None
     if world > 1 and args.mode_rows:
         inp_r = Input(text=c1_text(npoints))

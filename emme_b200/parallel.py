@@ -59,6 +59,49 @@ def gather_results(local, world=None):
     return [r for _, r in sorted(merged, key=lambda t: t[0])]
 
 
+def solve_scan_parallel(base_text, key, values, omega0, device=0, group=None):
+    """Scan-parallel driver (BASELINE config C5): `values` of the input key `key` are independent
+    scan points (each with the explicit start `omega0`, a complex or one per point); they are dealt
+    round-robin to the ranks of the process group, every rank solves its points with
+    solve_once_eigen on its own GPU, and the records {value, omega, iterations, status} are
+    gathered on every rank in scan order.  No collective touches the data path.
+
+    A failing point is recorded like the reference's scan does (src/main.cpp:300-318):
+    {"eigenvalue": "NaN", "reason": <message>}."""
+    import re
+
+    import torch.distributed as dist
+
+    from .solver import Input, solve_once_eigen
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    starts = list(omega0) if isinstance(omega0, (list, tuple)) else [omega0] * len(values)
+    local = []
+    solver = None
+    for k, v in scan_partition(list(values), rank, world):
+        rec = {"scan_value": v, "rank": rank}
+        try:
+            inp = Input(text=base_text)
+            inp.set_number(key, v)
+            if solver is None:
+                solver = EigenSolver.from_input(inp, device=device)
+            else:                                   # same mesh: reuse the handle and its buffers
+                p, _ = inp.params()
+                capi.check(solver._lib.emme_set_params(solver._h, p))
+                tabs = [np.ascontiguousarray(t) for t in inp.tables()]
+                capi.check(solver._lib.emme_set_tables(solver._h, *[t.ctypes.data for t in tabs]))
+                solver.synchronize()
+            w, iters, _ = solve_once_eigen(inp, starts[k], solver=solver)
+            rec.update(eigenvalue=[w.real, w.imag], iterations=len(iters),
+                       converged=abs(iters[-1][1]) < abs(inp.number("iteration_precision") * w))
+        except Exception as e:                       # noqa: BLE001 - recorded, scan continues
+            rec.update(eigenvalue="NaN", reason=str(e))
+        local.append((k, rec))
+    if solver is not None:
+        solver.close()
+    return gather_results(local)
+
+
 class _DevMatrix:
     """Zero-copy torch view of a handle-owned device matrix (for NCCL collectives)."""
 

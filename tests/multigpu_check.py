@@ -38,6 +38,14 @@ def main():
         ok = ok and same_w and same_A
         s.close()
         dist.barrier()
+    # scan-parallel: 6 independent k_rho points dealt to the ranks, gathered in scan order
+    base = (ROOT / "tests" / "golden" / "inputs" / "c1_n64.json").read_text()
+    ks = [0.25 + 0.02 * k for k in range(6)]
+    recs = parallel.solve_scan_parallel(base, "k_rho", ks, w0, device=local)
+    ok = ok and [r["scan_value"] for r in recs] == ks and all(r.get("converged") for r in recs)
+    ok = ok and sorted({r["rank"] for r in recs}) == list(range(min(world, 6)))
+    if rank == 0:
+        print("[scan]", [(r["scan_value"], r["rank"], r["iterations"], r["eigenvalue"]) for r in recs], flush=True)
     t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

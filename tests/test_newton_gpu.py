@@ -176,3 +176,20 @@ def test_trace_delta_tiny(dim, native_lib):
     d = s.trace_delta(A, B)
     ref = -1.0 / np.trace(np.linalg.solve(A, B))
     assert abs(d - ref) <= 1e-12 * abs(ref)
+
+
+def test_scan_parallel_single_rank_matches_reference_scan(native_lib):
+    """solve_scan_parallel on one rank: independent points with explicit starts reproduce the
+    eigenvalues of the reference program's continuation scan (same roots, 6 printed digits)."""
+    import json
+    from emme_b200 import parallel
+    gold = json.loads((cases.GOLD / "scan_c1_n32.json").read_text())
+    base = cases.input_path("c1_n32").read_text()
+    starts = [complex(*e) * (1 + 1e-3) for e in gold["eigenvalues"]]      # near each root
+    recs = parallel.solve_scan_parallel(base, "omega_d_coeff", gold["scan_values"], starts)
+    assert [r["scan_value"] for r in recs] == gold["scan_values"]
+    for r, (ra, rb) in zip(recs, gold["eigenvalues"]):
+        assert r["converged"], r
+        assert abs(r["eigenvalue"][0] - ra) < 2e-6 and abs(r["eigenvalue"][1] - rb) < 2e-6, (r, ra, rb)
+    bad = parallel.solve_scan_parallel(base.replace('"tokamak"', '"torus"'), "omega_d_coeff", [1.0], -0.8 + 0.25j)
+    assert bad[0]["eigenvalue"] == "NaN" and "not supported" in bad[0]["reason"]
