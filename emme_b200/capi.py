@@ -31,7 +31,8 @@ class EmmeStats(C.Structure):
     """struct emme_stats"""
     _fields_ = [(n, C.c_ulonglong) for n in
                 ("integrals", "panels", "evals", "fwd_trips", "bwd_trips", "max_stack")] + [
-        ("assemble_ms", C.c_double), ("dense_ms", C.c_double), ("launches", C.c_ulonglong), ("pivot_fallbacks", C.c_ulonglong)]
+        ("assemble_ms", C.c_double), ("dense_ms", C.c_double), ("launches", C.c_ulonglong), ("pivot_fallbacks", C.c_ulonglong),
+        ("sym_steps", C.c_ulonglong), ("dense_flops", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

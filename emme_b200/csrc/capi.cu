@@ -50,6 +50,8 @@ struct emme_solver {
     void* d_trig = nullptr;           // node table of kernel 1
     int spill_cap = 0, grid_blocks = 0;
     void* d_dense_ws = nullptr;
+    // symmetric dense path: M = L^-1, its scaled transpose, per-tile partial traces
+    void *Y = nullptr, *YT = nullptr, *d_sym_ws = nullptr;
     double2* d_trace = nullptr;
     int* d_info = nullptr;
     // Newton state
@@ -67,9 +69,10 @@ struct emme_solver {
     int optimistic = 1;               // try the interchange-free factorisation first
     int null_optimistic = 1;
     int use_graph = 1;                // replay the optimistic dense step as a CUDA graph
-    cudaGraphExec_t dense_graph = nullptr;
-    unsigned long long dense_graph_launches = 0;
-    unsigned long long pivot_fallbacks = 0;
+    int use_sym = 1;                  // try the symmetric (L D L^T, explicit inverse) path first
+    cudaGraphExec_t dense_graph = nullptr, sym_graph = nullptr;
+    unsigned long long dense_graph_launches = 0, sym_graph_launches = 0;
+    unsigned long long pivot_fallbacks = 0, sym_steps = 0;
     int* d_flag = nullptr;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
 };
@@ -146,10 +149,14 @@ int emme_destroy(emme_solver* s) {
     cudaFree(s->d_spill);
     cudaFree(s->d_trig);
     cudaFree(s->d_dense_ws);
+    cudaFree(s->Y);
+    cudaFree(s->YT);
+    cudaFree(s->d_sym_ws);
     cudaFree(s->d_trace);
     cudaFree(s->d_info);
     cudaFree(s->d_flag);
     if (s->dense_graph) cudaGraphExecDestroy(s->dense_graph);
+    if (s->sym_graph) cudaGraphExecDestroy(s->sym_graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -213,6 +220,7 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     if (const char* e = std::getenv("EMME_DENSE_OPTIMISTIC")) s->optimistic = std::atoi(e) != 0;
     if (const char* e = std::getenv("EMME_DENSE_TAU")) emme::dense_set_pivot_threshold(std::atof(e));
     if (const char* e = std::getenv("EMME_DENSE_GRAPH")) s->use_graph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("EMME_DENSE_SYM")) s->use_sym = std::atoi(e) != 0;
     *out = s.release();
     return 0;
 }
@@ -223,6 +231,11 @@ static int ensure_newton_buffers(emme_solver* s) {
     if (!s->Ad) CU(cudaMalloc(&s->Ad, s->bytes()));
     if (!s->W) CU(cudaMalloc(&s->W, s->bytes()));
     if (!s->d_dense_ws) CU(cudaMalloc(&s->d_dense_ws, emme::dense_workspace_bytes(s->dim)));
+    if (s->use_sym) {
+        if (!s->Y) CU(cudaMalloc(&s->Y, s->bytes()));
+        if (!s->YT) CU(cudaMalloc(&s->YT, s->bytes()));
+        if (!s->d_sym_ws) CU(cudaMalloc(&s->d_sym_ws, emme::dense_sym_workspace_bytes(s->dim)));
+    }
     return 0;
 }
 
@@ -285,10 +298,49 @@ int emme_assemble(emme_solver* s, double wr, double wi, void* host_out) {
 
 }  // extern "C" (templates below)
 
-// ---- dense step on (A, Ad): delta = -1/trace(A^-1 Ad); A is preserved, Ad destroyed ----
-// First the optimistic factorisation (no interchanges, verified against the partial-pivoting
-// criterion on the fly); if the verification fails, `restore_rhs` rebuilds Ad and the step is
-// repeated with the pivoting kernels.
+// ---- dense step on (A, Ad): delta = -1/trace(A^-1 Ad); A is preserved ----
+// Three paths, each verified on the device, tried in this order:
+//   0  symmetric: A = L D L^T without interchanges, trace from the explicit inverse (4 dim^3
+//      flops; Ad is only read).  Abandoned if A is not bitwise symmetric (flag bit 2) or partial
+//      pivoting would have interchanged rows (flag bit 1);
+//   1  optimistic LU of the augmented system (no interchanges, verified; Ad destroyed);
+//   2  LU with partial pivoting.
+// `restore_rhs` rebuilds Ad after a path that destroyed it.
+
+// Capture a fixed launch sequence on fixed buffers once, then replay it (the launch-bound loop).
+template <class Enqueue>
+static int replay_graph(emme_solver* s, cudaGraphExec_t* exec, unsigned long long* n_in_graph,
+                        Enqueue enqueue) {
+    if (!*exec && s->use_graph) {
+        cudaGraph_t g = nullptr;
+        unsigned long long nl = 0;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t le = enqueue(&nl);
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        if (le != cudaSuccess || ce != cudaSuccess || !g) {
+            cudaGetLastError();
+            s->use_graph = 0;          // capture not possible: fall back to plain launches
+            if (g) cudaGraphDestroy(g);
+        } else {
+            cudaError_t ie = cudaGraphInstantiate(exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) {
+                cudaGetLastError();
+                *exec = nullptr;
+                s->use_graph = 0;
+            }
+            *n_in_graph = nl;
+        }
+    }
+    if (s->use_graph && *exec) {
+        CU(cudaGraphLaunch(*exec, s->stream));
+        s->launches += *n_in_graph;
+    } else {
+        CU(enqueue(&s->launches));
+    }
+    return 0;
+}
+
 template <class RestoreRhs>
 static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
     cudaEvent_t e0, e1;
@@ -297,54 +349,63 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
     CU(cudaEventRecord(e0, s->stream));
     double tr[2];
     int info = 0, flag = 0;
-    for (int attempt = s->optimistic ? 0 : 1; attempt < 2; ++attempt) {
-        const int optimistic = attempt == 0;
-        if (attempt == 1 && s->optimistic) {
-            int rc = restore_rhs();
+    bool rhs_intact = true;
+    int path = (s->use_sym && s->Y) ? 0 : (s->optimistic ? 1 : 2);
+    const double d3 = (double)s->dim * s->dim * s->dim;
+    for (;;) {
+        if (path == 0) {
+            CU(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+            CU(emme::launch_sym_copy_check(s->A, s->W, s->dim, s->d_flag, s->stream, &s->launches));
+            int rc = replay_graph(s, &s->sym_graph, &s->sym_graph_launches, [&](unsigned long long* nl) {
+                return emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace,
+                                              s->d_info, s->d_flag, s->stream, nl);
+            });
             if (rc) return rc;
-            ++s->pivot_fallbacks;
-        }
-        CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
-        if (optimistic && s->use_graph) {
-            // The interchange-free path is a fixed sequence of ~5*dim/32 short launches on fixed
-            // buffers: captured once into a CUDA graph and replayed (the launch-bound inner loop).
-            if (!s->dense_graph) {
-                cudaGraph_t g = nullptr;
-                unsigned long long nl = 0;
-                CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-                cudaError_t le = emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace,
-                                                          s->d_info, s->stream, &nl, 1, s->d_flag);
-                cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
-                if (le != cudaSuccess || ce != cudaSuccess || !g) {
-                    cudaGetLastError();
-                    s->use_graph = 0;          // capture not possible: fall back to plain launches
-                    if (g) cudaGraphDestroy(g);
-                } else {
-                    cudaError_t ie = cudaGraphInstantiate(&s->dense_graph, g, 0);
-                    cudaGraphDestroy(g);
-                    if (ie != cudaSuccess) {
-                        cudaGetLastError();
-                        s->dense_graph = nullptr;
-                        s->use_graph = 0;
-                    }
-                    s->dense_graph_launches = nl;
-                }
-            }
-        }
-        if (optimistic && s->use_graph && s->dense_graph) {
-            CU(cudaGraphLaunch(s->dense_graph, s->stream));
-            s->launches += s->dense_graph_launches;
         } else {
-            CU(emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
-                                        s->stream, &s->launches, optimistic, s->d_flag));
+            if (!rhs_intact) {
+                int rc = restore_rhs();
+                if (rc) return rc;
+            }
+            rhs_intact = false;
+            CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
+            auto enqueue = [&](unsigned long long* nl) {
+                return emme::launch_trace_solve(s->W, s->Ad, s->dim, s->d_dense_ws, s->d_trace, s->d_info,
+                                                s->stream, nl, path == 1, s->d_flag);
+            };
+            if (path == 1) {
+                int rc = replay_graph(s, &s->dense_graph, &s->dense_graph_launches, enqueue);
+                if (rc) return rc;
+            } else {
+                CU(enqueue(&s->launches));
+            }
         }
         CU(cudaEventRecord(e1, s->stream));
         CU(cudaMemcpyAsync(tr, s->d_trace, sizeof tr, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));
-        if (optimistic)
-            CU(cudaMemcpyAsync(&flag, s->d_flag, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
+        flag = 0;
+        if (path < 2) CU(cudaMemcpyAsync(&flag, s->d_flag, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
-        if (!optimistic || flag == 0) break;
+        if (path == 0) {
+            if (flag == 0) {
+                ++s->sym_steps;
+                s->stats.dense_flops = 4.0 * d3;
+                break;
+            }
+            if ((flag & 1) || !s->optimistic) {
+                if (flag & 1) ++s->pivot_fallbacks;
+                path = 2;
+            } else {
+                path = 1;
+            }
+            continue;
+        }
+        s->stats.dense_flops = (8.0 / 3.0 + 4.0 + 2.0) * d3;
+        if (path == 1 && flag != 0) {
+            ++s->pivot_fallbacks;
+            path = 2;
+            continue;
+        }
+        break;
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -628,6 +689,7 @@ int emme_get_stats(const emme_solver* s, emme_stats* out) {
     *out = s->stats;
     out->launches = s->launches;
     out->pivot_fallbacks = s->pivot_fallbacks;
+    out->sym_steps = s->sym_steps;
     return 0;
 }
 

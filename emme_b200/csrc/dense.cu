@@ -511,16 +511,19 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
 // rate (37 TFLOP/s measured for both), but a DMMA carries 256 FMAs per issue slot instead of 32,
 // so the FP64 pipe stays fed (the DFMA version of this tile stalled at 60-64 % pipe utilisation).
 // k-slabs of 16 travel global -> shared memory with cp.async through a 3-stage ring.
-__device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
-                                               const z_t* __restrict__ A, int lda,
+struct GemmAcc {
+    double re[2][4][2], im[2][4][2];
+};
+
+// acc = A[m0:m0+64, 0:K) * Bm[0:K, n0:n0+64) (rows beyond M / columns beyond N read as zero)
+__device__ __forceinline__ void zgemm_mainloop(GemmAcc& acc, const z_t* __restrict__ A, int lda,
                                                const z_t* __restrict__ Bm, int ldb, int M, int N,
-                                               int K, int bx, int by) {
+                                               int K, int m0, int n0) {
     extern __shared__ __align__(16) unsigned char g_smem_raw[];
     z_t* smem = reinterpret_cast<z_t*>(g_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;          // warp grid 4 (M) x 2 (N)
-    const int m0 = by * GM, n0 = bx * GN;
     // staging ownership: A slab = 64 rows x 16 k, B slab = 16 k x 64 cols; 4 + 4 elements/thread
     const int ak = threadIdx.x & 15, am = threadIdx.x >> 4;      // A: rows am, am+16, am+32, am+48
     const int bn = threadIdx.x & 63, bk = threadIdx.x >> 6;      // B: k rows bk, bk+4, bk+8, bk+12
@@ -543,13 +546,12 @@ __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
             cp_async16(sB + k * G_LDB + bn, src, ok);
         }
     };
-    double acc_re[2][4][2], acc_im[2][4][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
-            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+            acc.re[i][j][0] = acc.re[i][j][1] = 0.0;
+            acc.im[i][j][0] = acc.im[i][j][1] = 0.0;
         }
 
     const int nslab = (K + GK - 1) / GK;
@@ -577,28 +579,48 @@ __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
                 const double nai = -af[i].y;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    dmma(acc_re[i][j], af[i].x, bf[j].x);
-                    dmma(acc_im[i][j], af[i].x, bf[j].y);
-                    dmma(acc_re[i][j], nai, bf[j].y);
-                    dmma(acc_im[i][j], af[i].y, bf[j].x);
+                    dmma(acc.re[i][j], af[i].x, bf[j].x);
+                    dmma(acc.im[i][j], af[i].x, bf[j].y);
+                    dmma(acc.re[i][j], nai, bf[j].y);
+                    dmma(acc.im[i][j], af[i].y, bf[j].x);
                 }
             }
         }
     }
     cp_async_wait<0>();
+    __syncthreads();   // the shared-memory ring may be reused by the caller / the next tile
+}
+
+// element (i, j, e) of a thread's accumulators is tile entry (acc_row(i), acc_col(j, e))
+__device__ __forceinline__ int acc_row(int i) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    return (warp & 3) * 16 + i * 8 + (lane >> 2);
+}
+__device__ __forceinline__ int acc_col(int j, int e) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    return (warp >> 2) * 32 + j * 8 + 2 * (lane & 3) + e;
+}
+
+__device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
+                                               const z_t* __restrict__ A, int lda,
+                                               const z_t* __restrict__ Bm, int ldb, int M, int N,
+                                               int K, int bx, int by) {
+    const int m0 = by * GM, n0 = bx * GN;
+    GemmAcc acc;
+    zgemm_mainloop(acc, A, lda, Bm, ldb, M, N, K, m0, n0);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const int m = m0 + wm * 16 + i * 8 + g;
+        const int m = m0 + acc_row(i);
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = n0 + wn * 32 + j * 8 + 2 * q + e;
+                const int n = n0 + acc_col(j, e);
                 if (n >= N) continue;
                 z_t c = C[(size_t)m * ldc + n];
-                c.x -= acc_re[i][j][e];
-                c.y -= acc_im[i][j][e];
+                c.x -= acc.re[i][j][e];
+                c.y -= acc.im[i][j][e];
                 C[(size_t)m * ldc + n] = c;
             }
         }
@@ -624,6 +646,274 @@ zgemm_sub2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int N1, int 
         zgemm_sub_tile(C2, ld, A, ld, B2, ld, M, N2, K, blockIdx.x - nx1, blockIdx.y);
 }
 
+// ------------------------------------------------------------------ symmetric path: kernels
+// EMME's matrix is complex SYMMETRIC (include/solver.h:448-453, :494-504 write every entry together
+// with its mirror).  Without interchanges A = L D L^T, i.e. the U factor is D L^T, and
+//     trace(A^-1 B) = sum_ij (A^-1)_ij B_ji,   A^-1 = M^T D^-1 M,   M = L^-1,
+// which needs 4 dim^3 real flops (factor 4/3, M 4/3, lower triangle of M^T D^-1 M 4/3) instead of
+// the (8/3 + 4 + 2) dim^3 of LU + forward elimination of dim right-hand sides + half a back
+// substitution.  launch_trace_sym below drives these kernels; symmetry and "partial pivoting
+// keeps the diagonal" are both VERIFIED on the device (flag bits 2 and 1) and the caller falls
+// back to the general LU path when either fails.
+
+// W <- A on the lower block triangle (64 x 64 blocks; diagonal blocks completely) and check that A
+// equals its transpose bit for bit.  32 x 32 tiles, block (32, 8).
+__global__ void __launch_bounds__(256)
+sym_copy_check_kernel(const z_t* __restrict__ A, z_t* __restrict__ W, int dim, int* __restrict__ flag) {
+    __shared__ z_t t[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if ((bj >> 1) > (bi >> 1)) return;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = bj * 32 + r, j = bi * 32 + threadIdx.x;     // mirror tile
+        t[r][threadIdx.x] = (i < dim && j < dim) ? A[(size_t)i * dim + j] : make_double2(0., 0.);
+    }
+    __syncthreads();
+    int bad = 0;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + threadIdx.x;
+        if (i < dim && j < dim) {
+            const z_t v = A[(size_t)i * dim + j];
+            const z_t m = t[threadIdx.x][r];                      // A[j][i]
+            if (v.x != m.x || v.y != m.y) bad = 1;
+            W[(size_t)i * dim + j] = v;
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0 && threadIdx.y == 0) atomicOr(flag, 2);
+}
+
+__global__ void set_identity_diag_kernel(z_t* __restrict__ Y, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dim) Y[(size_t)i * dim + i] = make_double2(1., 0.);
+}
+
+// One launch per NB-wide panel [k0, k0+jb):
+//   CTAs [0, n_row_ctas): one thread per row r below k0.  Every CTA factors the jb x jb diagonal
+//     block redundantly in shared memory (as panel_nopiv_kernel), then each thread eliminates its
+//     row against it: L[r, k0:ke) = A[r, k0:ke) U11^-1, checks the partial-pivoting criterion, and
+//     also writes the block row of U by symmetry, U[k0+c, r] = L[r, k0+c] * u_cc  (U12 = D L21^T),
+//     which replaces the block-row solve of the general path;
+//   CTAs [n_row_ctas, ..): one thread per column c < ycols of Y: Y[k0:ke, c] <- L11^-1 Y[k0:ke, c]
+//     (the identity carried along: rows k0..ke of M = L^-1 become final).
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
+panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int k0, int jb, int ycols,
+                 int n_row_ctas, double tau, int* __restrict__ flag, int* __restrict__ info) {
+    __shared__ z_t sD[NB][NB + 1];     // diagonal block: strict lower = L11, upper = U11
+    __shared__ z_t sInv[NB];           // 1/u_cc
+    __shared__ double sAbs[NB];        // |u_cc| (cabs1)
+    for (int e = threadIdx.x; e < NB * NB; e += TPB) {
+        const int rr = e / NB, cc = e % NB;
+        sD[rr][cc] = (rr < jb && cc < jb) ? W[(size_t)(k0 + rr) * ld + k0 + cc] : make_double2(0., 0.);
+    }
+    __syncthreads();
+    int bad = 0;
+    if (threadIdx.x < 32) {
+        const int i = threadIdx.x;     // lane = row of the diagonal block, kept in registers
+        z_t row[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) row[k] = sD[i][k];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            if (c < jb) {
+                // row c is final: its owner has already written it back (see below)
+                const z_t u = sD[c][c];
+                const double ua = fabs(u.x) + fabs(u.y);
+                const z_t inv = ua > 0.0 ? zrecip(u) : make_double2(0., 0.);
+                if (i == 0) {
+                    sInv[c] = inv;
+                    sAbs[c] = ua;
+                    if (ua == 0.0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + c + 1);
+                }
+                if (i > c && i < jb) {
+                    if (fabs(row[c].x) + fabs(row[c].y) > tau * ua) bad = 1;
+                    const z_t l = zmul(row[c], inv);
+                    row[c] = l;
+#pragma unroll
+                    for (int k = c + 1; k < NB; ++k) zfms(row[k], l, sD[c][k]);
+                }
+                if (i == c + 1) {
+                    // the next pivot row is complete: publish it
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) sD[i][k] = row[k];
+                }
+                __syncwarp();
+            }
+        }
+        // rows > publish point already stored when they became pivot rows; row 0 never changed
+    }
+    __syncthreads();
+    if ((int)blockIdx.x < n_row_ctas) {
+        const int r = blockIdx.x * TPB + threadIdx.x;      // row offset below k0
+        if (r < dim - k0) {
+            z_t* myrow = W + (size_t)(k0 + r) * ld + k0;
+            if (r < jb) {
+                // rows of the diagonal block: CTA 0 writes the factored block back
+                if (blockIdx.x == 0) {
+                    for (int c = 0; c < jb; ++c) myrow[c] = sD[r][c];
+                }
+            } else {
+                z_t a[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) a[k] = k < jb ? myrow[k] : make_double2(0., 0.);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    if (c < jb) {
+                        if (fabs(a[c].x) + fabs(a[c].y) > tau * sAbs[c]) bad = 1;
+                        const z_t l = zmul(a[c], sInv[c]);
+                        a[c] = l;
+#pragma unroll
+                        for (int k = c + 1; k < NB; ++k) zfms(a[k], l, sD[c][k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    if (k < jb) myrow[k] = a[k];
+                // U[k0+c, k0+r] = l_rc * u_cc: coalesced across the threads of a warp
+                z_t* ucol = W + (size_t)k0 * ld + k0 + r;
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < jb) ucol[(size_t)c * ld] = zmul(a[c], sD[c][c]);
+            }
+        }
+    } else {
+        const int col = ((int)blockIdx.x - n_row_ctas) * TPB + threadIdx.x;
+        if (col < ycols) {
+            z_t* M = Y + col;
+            z_t x[NB];
+#pragma unroll
+            for (int rr = 0; rr < NB; ++rr) x[rr] = rr < jb ? M[(size_t)(k0 + rr) * ld] : make_double2(0., 0.);
+#pragma unroll
+            for (int rr = 1; rr < NB; ++rr) {
+#pragma unroll
+                for (int cc = 0; cc < rr; ++cc) zfms(x[rr], sD[rr][cc], x[cc]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < NB; ++rr)
+                if (rr < jb) M[(size_t)(k0 + rr) * ld] = x[rr];
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// Trailing update of the symmetric path in ONE launch: C1 -= A*B1 on the LOWER block triangle only
+// (tiles with column tile <= row tile; C1's origin lies on the diagonal of W), C2 -= A*B2 (rows of
+// Y) everywhere.  The two products share A but may have different row counts.
+__global__ void __launch_bounds__(256, 2)
+zgemm_sym2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int M1, int N1, int nx1,
+                  z_t* __restrict__ C2, const z_t* __restrict__ B2, int M2, int N2, int ld,
+                  const z_t* __restrict__ A, int K) {
+    const int by = blockIdx.y;
+    if ((int)blockIdx.x < nx1) {
+        const int bx = blockIdx.x;
+        if (bx > by || by * GM >= M1) return;
+        zgemm_sub_tile(C1, ld, A, ld, B1, ld, M1, N1, K, bx, by);
+    } else {
+        if (by * GM >= M2) return;
+        zgemm_sub_tile(C2, ld, A, ld, B2, ld, M2, N2, K, blockIdx.x - nx1, by);
+    }
+}
+
+// YT(i, k) = Y(k, i) / d_k for k >= i (d = diag of the factored W), zero below the diagonal (only
+// the diagonal 64-blocks are ever read there).  32 x 32 tiles, block (32, 8).
+__global__ void __launch_bounds__(256)
+transpose_invd_kernel(const z_t* __restrict__ Y, const z_t* __restrict__ W, z_t* __restrict__ YT, int dim) {
+    __shared__ z_t t[32][33];
+    const int bi = blockIdx.y, bk = blockIdx.x;
+    if (bk < bi) {
+        if ((bk >> 1) == (bi >> 1)) {
+            for (int r = threadIdx.y; r < 32; r += 8) {
+                const int i = bi * 32 + r, k = bk * 32 + threadIdx.x;
+                if (i < dim && k < dim) YT[(size_t)i * dim + k] = make_double2(0., 0.);
+            }
+        }
+        return;
+    }
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int k = bk * 32 + r, i = bi * 32 + threadIdx.x;
+        z_t v = make_double2(0., 0.);
+        if (k < dim && i < dim && k >= i) v = zmul(Y[(size_t)k * dim + i], zrecip(W[(size_t)k * dim + k]));
+        t[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = bi * 32 + r, k = bk * 32 + threadIdx.x;
+        if (i < dim && k < dim) YT[(size_t)i * dim + k] = t[threadIdx.x][r];
+    }
+}
+
+// partial[t] = sum over tile t = (I, J), I >= J, of P_ij * (I > J ? B_ij + B_ji : B_ji) with
+// P = YT * Y = A^-1 (only k >= 64 I contributes: YT is upper, Y lower triangular).
+__global__ void __launch_bounds__(256, 2)
+ptrace_kernel(const z_t* __restrict__ YT, const z_t* __restrict__ Y, const z_t* __restrict__ Bd, int dim,
+              z_t* __restrict__ partial) {
+    __shared__ double red[2][8];
+    const int t = blockIdx.x;
+    int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int kstart = I * GM;
+    GemmAcc acc;
+    zgemm_mainloop(acc, YT + kstart, dim, Y + (size_t)kstart * dim, dim, dim, dim, dim - kstart, I * GM,
+                   J * GN);
+    double sr = 0., si = 0.;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = I * GM + acc_row(i);
+        if (m >= dim) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = J * GN + acc_col(j, e);
+                if (n >= dim) continue;
+                z_t b = Bd[(size_t)n * dim + m];
+                if (I != J) {
+                    const z_t b2 = Bd[(size_t)m * dim + n];
+                    b.x += b2.x;
+                    b.y += b2.y;
+                }
+                const double pr = acc.re[i][j][e], pi = acc.im[i][j][e];
+                sr += pr * b.x - pi * b.y;
+                si += pr * b.y + pi * b.x;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = sr; red[1][warp] = si; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0., y = 0.;
+        for (int w = 0; w < 8; ++w) { x += red[0][w]; y += red[1][w]; }
+        partial[t] = make_double2(x, y);
+    }
+}
+
+__global__ void reduce_partials_kernel(const z_t* __restrict__ partial, int n, z_t* __restrict__ out) {
+    __shared__ double sx[256], sy[256];
+    double x = 0., y = 0.;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        x += partial[i].x;
+        y += partial[i].y;
+    }
+    sx[threadIdx.x] = x;
+    sy[threadIdx.x] = y;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sx[threadIdx.x] += sx[threadIdx.x + o];
+            sy[threadIdx.x] += sy[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = make_double2(sx[0], sy[0]);
+}
+
 static cudaError_t gemm_setup() {
     static bool done = false;
     if (done) return cudaSuccess;
@@ -632,6 +922,11 @@ static cudaError_t gemm_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(zgemm_sub2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)G_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zgemm_sym2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)G_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ptrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
@@ -940,6 +1235,90 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
     }
     trace_kernel<<<1, 256, 0, stream>>>(B, ld, dim, (z_t*)d_trace);
     if (n_launches) *n_launches += nl + 1;
+    return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------ symmetric path: driver
+size_t dense_sym_workspace_bytes(int dim) {
+    const size_t nt = (dim + GM - 1) / GM;
+    return sizeof(z_t) * (nt * (nt + 1) / 2) + 64;
+}
+
+// W <- A (lower block triangle) + bitwise symmetry check (raises bit 2 of *d_flag).  Kept apart
+// from launch_trace_sym because A alternates between two buffers while the rest of the step
+// works on fixed buffers and is replayed as a CUDA graph.
+cudaError_t launch_sym_copy_check(const void* A, void* W, int dim, int* d_flag, cudaStream_t stream,
+                                  unsigned long long* n_launches) {
+    const int nt = (dim + 31) / 32;
+    sym_copy_check_kernel<<<dim3(nt, nt), dim3(32, 8), 0, stream>>>((const z_t*)A, (z_t*)W, dim, d_flag);
+    if (n_launches) ++*n_launches;
+    return cudaGetLastError();
+}
+
+// trace(A^-1 B) for complex symmetric A, W holding A's lower block triangle (destroyed: on return
+// W holds the complete L\U factors), Y and YT dim x dim scratch, B read only.  Raises bit 1 of
+// *d_flag when partial pivoting would have interchanged rows (the caller then repeats the step with
+// the pivoting LU).  *d_flag is NOT cleared here.
+cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int dim, void* sym_workspace,
+                             void* d_trace, int* d_info, int* d_flag, cudaStream_t stream,
+                             unsigned long long* n_launches) {
+    unsigned long long nl = 0;
+    z_t* W = (z_t*)Wv;
+    z_t* Y = (z_t*)Yv;
+    z_t* YT = (z_t*)YTv;
+    const int ld = dim;
+    cudaError_t e = gemm_setup();
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d_info, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(Y, 0, sizeof(z_t) * (size_t)dim * dim, stream);
+    if (e != cudaSuccess) return e;
+    set_identity_diag_kernel<<<(dim + 255) / 256, 256, 0, stream>>>(Y, dim);
+    ++nl;
+    const int NBO = g_nbo > 0 ? g_nbo : (dim <= 2048 ? NB : 128);
+    auto at = [&](z_t* M, int r, int c) { return M + (size_t)r * ld + c; };
+    // C1 = W[r1:, c1:c1+N1) (lower block triangle), C2 = Y[r1:r1+M2, 0:N2), A = W[r1:, kb:kb+K)
+    auto update = [&](int r1, int M1, int c1, int N1, int M2, int N2, int kb, int K) {
+        const int M = M1 > M2 ? M1 : M2;
+        if (M <= 0) return;
+        const int nx1 = M1 > 0 ? (N1 + GN - 1) / GN : 0, nx2 = M2 > 0 ? (N2 + GN - 1) / GN : 0;
+        if (nx1 + nx2 == 0) return;
+        dim3 g(nx1 + nx2, (M + GM - 1) / GM);
+        zgemm_sym2_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(at(W, r1, c1), at(W, kb, c1), M1, N1, nx1,
+                                                            at(Y, r1, 0), at(Y, kb, 0), M2, N2, ld,
+                                                            at(W, r1, kb), K);
+        ++nl;
+    };
+    for (int K0 = 0; K0 < dim; K0 += NBO) {
+        const int JB = dim - K0 < NBO ? dim - K0 : NBO;
+        const int KE = K0 + JB;
+        for (int k0 = K0; k0 < KE; k0 += NB) {
+            const int jb = KE - k0 < NB ? KE - k0 : NB;
+            const int ke = k0 + jb;
+            const int n_row = (dim - k0 + 127) / 128, n_col = (ke + 127) / 128;
+            panel_sym_kernel<128><<<n_row + n_col, 128, 0, stream>>>(W, Y, ld, dim, k0, jb, ke, n_row, g_tau,
+                                                                     d_flag, d_info);
+            ++nl;
+            // inside the outer block: columns [ke, KE) of W below the panel, rows [ke, KE) of Y
+            if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, ke, k0, jb);
+        }
+        // everything below the outer block: rank-JB update
+        if (KE < dim) update(KE, dim - KE, KE, dim - KE, dim - KE, KE, K0, JB);
+    }
+    // A^-1 = M^T D^-1 M on the lower block triangle, contracted with B on the fly
+    {
+        const int nt32 = (dim + 31) / 32;
+        transpose_invd_kernel<<<dim3(nt32, nt32), dim3(32, 8), 0, stream>>>(Y, W, YT, dim);
+        ++nl;
+        const int nt = (dim + GM - 1) / GM;
+        const int ntiles = nt * (nt + 1) / 2;
+        ptrace_kernel<<<ntiles, 256, G_SMEM_BYTES, stream>>>(YT, Y, (const z_t*)Bv, dim, (z_t*)sym_workspace);
+        ++nl;
+        reduce_partials_kernel<<<1, 256, 0, stream>>>((const z_t*)sym_workspace, ntiles, (z_t*)d_trace);
+        ++nl;
+    }
+    if (n_launches) *n_launches += nl;
     return cudaGetLastError();
 }
 

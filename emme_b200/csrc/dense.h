@@ -22,6 +22,16 @@ cudaError_t launch_solve_factored(const void* W, void* B, int dim, int nrhs, voi
                                   int optimistic, cudaStream_t stream, unsigned long long* n_launches);
 cudaError_t launch_conj_normalise(const void* X, int ld, int dim, void* rhs, int rhs_ld, double* norm_out,
                                   int conjugate, cudaStream_t stream);
+// ---- symmetric path (complex symmetric A, no interchanges): trace(A^-1 B) from
+// A^-1 = M^T D^-1 M with A = L D L^T, M = L^-1 -- 4 dim^3 real flops instead of 26/3 dim^3.
+// *d_flag bits: 1 = partial pivoting would have interchanged rows, 2 = A is not symmetric; either
+// one means the result must be discarded and the step repeated with launch_trace_solve.
+size_t dense_sym_workspace_bytes(int dim);
+cudaError_t launch_sym_copy_check(const void* A, void* W, int dim, int* d_flag, cudaStream_t stream,
+                                  unsigned long long* n_launches);
+cudaError_t launch_trace_sym(void* W, void* Y, void* YT, const void* B, int dim, void* sym_workspace,
+                             void* d_trace, int* d_info, int* d_flag, cudaStream_t stream,
+                             unsigned long long* n_launches);
 void dense_set_pivot_threshold(double tau);
 // Ad = (A - Aold)/delta over n complex entries
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,

@@ -59,6 +59,8 @@ typedef struct emme_stats {
     double dense_ms;              /* CUDA-event time of the last dense step         */
     unsigned long long launches;  /* kernels launched by this handle since creation */
     unsigned long long pivot_fallbacks; /* dense steps repeated with row interchanges   */
+    unsigned long long sym_steps; /* dense steps completed on the symmetric (L D L^T) path */
+    double dense_flops;           /* real flops of the last dense step (path that ran)     */
 } emme_stats;
 
 typedef struct emme_solver emme_solver; /* opaque; owns device memory */

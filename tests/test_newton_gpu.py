@@ -25,6 +25,101 @@ def test_trace_delta_matches_numpy(dim, native_lib):
     assert abs(d - ref) <= 1e-10 * abs(ref), (d, ref)
 
 
+def _sym_case(dim, seed=0, general_rhs=False):
+    """Complex SYMMETRIC, diagonally strong A (the shape of EMME's matrices) and a right-hand side."""
+    rng = np.random.default_rng(1000 * seed + dim)
+    S = (rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))) * (0.4 / np.sqrt(dim))
+    A = S + S.T + np.diag(2.0 + 0.3 * rng.standard_normal(dim) + 0.2j * rng.standard_normal(dim))
+    B = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    if not general_rhs:
+        B = B + B.T
+    return A, B
+
+
+def _trace_solver(dim):
+    inp = Input(cases.input_path("c1_n32"))
+    p, _ = inp.params()
+    return EigenSolver(p, dim, np.linspace(-1, 1, dim), np.zeros(dim), np.ones(dim))
+
+
+@pytest.mark.parametrize("dim", [2, 5, 31, 32, 33, 64, 65, 100, 191, 256, 257, 640, 1000])
+def test_symmetric_path_matches_numpy(dim, native_lib):
+    """Symmetric path of kernel 2 (A = L D L^T, trace from the explicit inverse): taken for a
+    symmetric, diagonally strong matrix, and delta agrees with numpy's LU solve.  Ragged sizes
+    exercise every tile edge of the masked GEMMs."""
+    A, B = _sym_case(dim)
+    s = _trace_solver(dim)
+    d = s.trace_delta(A, B)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    st = s.stats()
+    assert st["sym_steps"] == 1 and st["pivot_fallbacks"] == 0, st
+    assert abs(d - ref) <= 1e-12 * abs(ref), (d, ref)
+    # a second call replays the captured CUDA graph
+    d2 = s.trace_delta(A, B)
+    assert d2 == d and s.stats()["sym_steps"] == 2
+
+
+@pytest.mark.parametrize("dim", [2100, 2304])
+def test_symmetric_path_two_level_blocking(dim, native_lib):
+    """dim > 2048 switches kernel 2 to 128-wide outer blocks (ragged and aligned sizes)."""
+    A, B = _sym_case(dim, seed=1)
+    s = _trace_solver(dim)
+    d = s.trace_delta(A, B)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    assert s.stats()["sym_steps"] == 1
+    assert abs(d - ref) <= 1e-12 * abs(ref), (d, ref)
+
+
+def test_symmetric_path_general_rhs(native_lib):
+    """The contraction sum_ij (A^-1)_ij B_ji does not need a symmetric right-hand side."""
+    A, B = _sym_case(300, seed=2, general_rhs=True)
+    s = _trace_solver(300)
+    d = s.trace_delta(A, B)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    assert s.stats()["sym_steps"] == 1
+    assert abs(d - ref) <= 1e-12 * abs(ref), (d, ref)
+
+
+def test_symmetric_path_is_verified(native_lib):
+    """The symmetric path checks its own preconditions on the device: one asymmetric entry (last
+    bit) sends the step to the LU path, a symmetric matrix that needs interchanges to the pivoting
+    LU; both still give the right delta."""
+    A, B = _sym_case(200, seed=3)
+    s = _trace_solver(200)
+    A1 = A.copy()
+    A1[150, 3] = np.nextafter(A1[150, 3].real, 10.0) + 1j * A1[150, 3].imag
+    d = s.trace_delta(A1, B)
+    st = s.stats()
+    assert st["sym_steps"] == 0 and st["pivot_fallbacks"] == 0, st
+    assert abs(d + 1.0 / np.trace(np.linalg.solve(A1, B))) <= 1e-12 * abs(d)
+    A2 = A.copy()
+    A2[7, 7] = 1e-9                      # symmetric, but partial pivoting must interchange row 7
+    d = s.trace_delta(A2, B)
+    st = s.stats()
+    assert st["sym_steps"] == 0 and st["pivot_fallbacks"] == 1, st
+    assert abs(d + 1.0 / np.trace(np.linalg.solve(A2, B))) <= 1e-10 * abs(d)
+    d = s.trace_delta(A, B)
+    assert s.stats()["sym_steps"] == 1
+    assert abs(d + 1.0 / np.trace(np.linalg.solve(A, B))) <= 1e-12 * abs(d)
+
+
+def test_symmetric_and_lu_paths_agree_on_real_matrices(golden, native_lib, monkeypatch):
+    """Same EMME matrices through both paths of kernel 2 (EMME_DENSE_SYM=0 disables the symmetric one)."""
+    inp = Input(cases.input_path("c1_em_n64"))
+    s = EigenSolver.from_input(inp)
+    A = s.matrixAssembler(-0.8 + 0.25j).copy()
+    A2 = s.matrixAssembler(-0.79 + 0.251j).copy()
+    Ad = (A - A2) / (0.01 - 0.001j)
+    d_sym = s.trace_delta(A, Ad)
+    assert s.stats()["sym_steps"] == 1
+    monkeypatch.setenv("EMME_DENSE_SYM", "0")
+    s2 = EigenSolver.from_input(inp)
+    d_lu = s2.trace_delta(A, Ad)
+    assert s2.stats()["sym_steps"] == 0
+    ref = -1.0 / np.trace(np.linalg.solve(A, Ad))
+    assert abs(d_sym - ref) <= 1e-12 * abs(ref) and abs(d_lu - ref) <= 1e-12 * abs(ref), (d_sym, d_lu, ref)
+
+
 def test_trace_delta_matches_oracle_on_real_matrices(golden, native_lib):
     import oracle_lib as O
     inp = Input(cases.input_path("c1_n128"))
