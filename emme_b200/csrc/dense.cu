@@ -656,6 +656,8 @@ zgemm_sub2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int N1, int 
 // keeps the diagonal" are both VERIFIED on the device (flag bits 2 and 1) and the caller falls
 // back to the general LU path when either fails.
 
+constexpr int PTRACE_MAX_CHUNKS = 8;   // split-K factor of ptrace_kernel on small systems
+
 // W <- A on the lower block triangle (64 x 64 blocks; diagonal blocks completely) and check that A
 // equals its transpose bit for bit.  32 x 32 tiles, block (32, 8).
 __global__ void __launch_bounds__(256)
@@ -686,113 +688,226 @@ __global__ void set_identity_diag_kernel(z_t* __restrict__ Y, int dim) {
     if (i < dim) Y[(size_t)i * dim + i] = make_double2(1., 0.);
 }
 
-// One launch per NB-wide panel [k0, k0+jb):
-//   CTAs [0, n_row_ctas): one thread per row r below k0.  Every CTA factors the jb x jb diagonal
-//     block redundantly in shared memory (as panel_nopiv_kernel), then each thread eliminates its
-//     row against it: L[r, k0:ke) = A[r, k0:ke) U11^-1, checks the partial-pivoting criterion, and
-//     also writes the block row of U by symmetry, U[k0+c, r] = L[r, k0+c] * u_cc  (U12 = D L21^T),
-//     which replaces the block-row solve of the general path;
-//   CTAs [n_row_ctas, ..): one thread per column c < ycols of Y: Y[k0:ke, c] <- L11^-1 Y[k0:ke, c]
-//     (the identity carried along: rows k0..ke of M = L^-1 become final).
-template <int TPB>
-__global__ void __launch_bounds__(TPB)
+// 1/a for well-scaled a (one division); Smith's form otherwise
+__device__ __forceinline__ z_t zrecip_fast(z_t a) {
+    const double n = a.x * a.x + a.y * a.y;
+    if (n > 1e-280 && n < 1e280) {
+        const double d = __drcp_rn(n);
+        return make_double2(a.x * d, -a.y * d);
+    }
+    return zrecip(a);
+}
+
+// One launch per NB-wide panel [k0, k0+jb).  Small code, no per-thread register rows (the
+// unrolled one-thread-per-row elimination of panel_nopiv_kernel is instruction-fetch bound: every
+// instruction executes once), tensor cores for the two block products:
+//   1. every CTA requests its 64 x 32 (or 32 x 64) operand tile with cp.async, then factors the
+//      jb x jb diagonal block redundantly in shared memory while the tile is in flight: all 128
+//      threads, thread (row i = t/4, columns k = t%4 + 4e), one barrier per pivot.  The identity is
+//      carried along (Gauss-Jordan on the lower part), so the block ends as L11 \ U11 in sD and
+//      Mi = L11^-1 (explicit unit diagonal, zeros above) in sM;
+//   2. row CTAs [0, n_row_ctas): T = A21 Mi^T on the FP64 tensor cores.  U11 = D L11^T (symmetry)
+//      makes T[r][c] the entry a_rc just before column c is eliminated, hence
+//         L[r, c] = T[r][c] / u_cc,   U[k0+c, r] = T[r][c]   (U12 = D L21^T: no block-row solve)
+//      and |T[r][c]| <= tau |u_cc| is the partial-pivoting check;
+//   3. column CTAs: rows k0..ke of Y <- Mi Y (the identity carried along: rows k0..ke of
+//      M = L^-1 become final), 64 columns of Y per CTA.
+constexpr int PS_ROWS = 64;                       // rows (row role) / columns (Y role) per CTA
+constexpr int PS_LD = NB + 4;                     // stride of sD, sM, row tile: 4 (mod 8) elements
+constexpr int PS_LDY = PS_ROWS + 2;               // stride of the Y tile: 2 (mod 8) elements
+constexpr int PS_TILE = PS_ROWS * PS_LD > NB * PS_LDY ? PS_ROWS * PS_LD : NB * PS_LDY;
+constexpr size_t PS_SMEM_BYTES = sizeof(z_t) * (2 * NB * PS_LD + PS_TILE) + sizeof(z_t) * NB + sizeof(double) * NB;
+
+#ifdef EMME_PS_CLOCKS
+__device__ long long g_ps_clocks[8];   // scratch/panel_bench.cu: phase boundaries of CTA 0
+#define PS_CLOCK(n) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_ps_clocks[n] = clock64(); } while (0)
+#else
+#define PS_CLOCK(n) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(128)
 panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int k0, int jb, int ycols,
                  int n_row_ctas, double tau, int* __restrict__ flag, int* __restrict__ info) {
-    __shared__ z_t sD[NB][NB + 1];     // diagonal block: strict lower = L11, upper = U11
-    __shared__ z_t sInv[NB];           // 1/u_cc
-    __shared__ double sAbs[NB];        // |u_cc| (cabs1)
-    for (int e = threadIdx.x; e < NB * NB; e += TPB) {
+    static_assert(NB == 32, "thread mapping of the diagonal-block factorisation");
+    extern __shared__ __align__(16) unsigned char ps_smem_raw[];
+    z_t* sD = reinterpret_cast<z_t*>(ps_smem_raw);   // [NB][PS_LD]
+    z_t* sM = sD + NB * PS_LD;                        // [NB][PS_LD]
+    z_t* sT = sM + NB * PS_LD;                        // operand tile
+    z_t* sInv = sT + PS_TILE;                         // 1/u_cc
+    double* sAbs = reinterpret_cast<double*>(sInv + NB);   // |u_cc| (cabs1)
+    const int tid = threadIdx.x;
+    PS_CLOCK(0);
+    const bool row_role = (int)blockIdx.x < n_row_ctas;
+    const int r0 = jb + (int)blockIdx.x * PS_ROWS;                      // first row offset below k0
+    const int c0 = ((int)blockIdx.x - n_row_ctas) * PS_ROWS;            // first column of Y
+    // ---- request the operand tile first: it lands while the diagonal block is factored ----
+    if (row_role) {
+        // rows r0 .. r0+63 of the panel, 32 columns each (one 512-byte row per warp instruction)
+#pragma unroll 4
+        for (int it = 0; it < PS_ROWS / 4; ++it) {
+            const int rr = (tid >> 5) + 4 * it, cc = tid & 31;
+            const bool ok = (k0 + r0 + rr < dim) && cc < jb;
+            const z_t* src = ok ? W + (size_t)(k0 + r0 + rr) * ld + k0 + cc : W;
+            cp_async16(sT + rr * PS_LD + cc, src, ok);
+        }
+    } else {
+#pragma unroll 4
+        for (int it = 0; it < NB / 2; ++it) {
+            const int kk = (tid >> 6) + 2 * it, nn = tid & 63;
+            const bool ok = kk < jb && (c0 + nn < ycols);
+            const z_t* src = ok ? Y + (size_t)(k0 + kk) * ld + c0 + nn : Y;
+            cp_async16(sT + kk * PS_LDY + nn, src, ok);
+        }
+    }
+    cp_async_commit();
+    for (int e = tid; e < NB * NB; e += 128) {
         const int rr = e / NB, cc = e % NB;
-        sD[rr][cc] = (rr < jb && cc < jb) ? W[(size_t)(k0 + rr) * ld + k0 + cc] : make_double2(0., 0.);
+        sD[rr * PS_LD + cc] = (rr < jb && cc < jb) ? W[(size_t)(k0 + rr) * ld + k0 + cc] : make_double2(0., 0.);
+        sM[rr * PS_LD + cc] = make_double2(rr == cc ? 1. : 0., 0.);
     }
     __syncthreads();
+    PS_CLOCK(1);
     int bad = 0;
-    if (threadIdx.x < 32) {
-        const int i = threadIdx.x;     // lane = row of the diagonal block, kept in registers
-        z_t row[NB];
+    {
+        const int i = tid >> 2, q = tid & 3;
+        for (int c = 0; c < jb; ++c) {
+            const z_t u = sD[c * PS_LD + c];
+            const double ua = fabs(u.x) + fabs(u.y);
+            const z_t inv = ua > 0.0 ? zrecip_fast(u) : make_double2(0., 0.);
+            if (tid == 0) {
+                sInv[c] = inv;
+                sAbs[c] = ua;
+                if (ua == 0.0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + c + 1);
+            }
+            const bool act = i > c && i < jb;
+            // Branch-free update of this thread's 8 entries of row i: columns k > c live in sD (the
+            // Schur complement), columns k <= c in sM (the identity carried along; sM[c][c] = 1 and
+            // sM[i][c] = 0 make column c come out as -l without a special case).  All 16 shared-memory
+            // loads are issued before the reciprocal is needed.
+            z_t x[NB / 4], pv[NB / 4];
 #pragma unroll
-        for (int k = 0; k < NB; ++k) row[k] = sD[i][k];
+            for (int e = 0; e < NB / 4; ++e) {
+                const int k = q + 4 * e;
+                const z_t* src = k > c ? sD : sM;
+                x[e] = src[i * PS_LD + k];
+                pv[e] = src[c * PS_LD + k];
+            }
+            const z_t num = sD[i * PS_LD + c];
+            __syncwarp();   // the four threads of a row have read a_ic before one of them overwrites it
+            if (act) {
+                const z_t l = zmul(num, inv);
+                if (q == 0 && fabs(num.x) + fabs(num.y) > tau * ua) bad = 1;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) {
-            if (c < jb) {
-                // row c is final: its owner has already written it back (see below)
-                const z_t u = sD[c][c];
-                const double ua = fabs(u.x) + fabs(u.y);
-                const z_t inv = ua > 0.0 ? zrecip(u) : make_double2(0., 0.);
-                if (i == 0) {
-                    sInv[c] = inv;
-                    sAbs[c] = ua;
-                    if (ua == 0.0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + c + 1);
+                for (int e = 0; e < NB / 4; ++e) zfms(x[e], l, pv[e]);
+#pragma unroll
+                for (int e = 0; e < NB / 4; ++e) {
+                    const int k = q + 4 * e;
+                    z_t* dst = k > c ? sD : sM;
+                    dst[i * PS_LD + k] = x[e];
                 }
-                if (i > c && i < jb) {
-                    if (fabs(row[c].x) + fabs(row[c].y) > tau * ua) bad = 1;
-                    const z_t l = zmul(row[c], inv);
-                    row[c] = l;
+                if (q == (c & 3)) sD[i * PS_LD + c] = l;
+            }
+            __syncthreads();
+        }
+    }
+    PS_CLOCK(2);
+    cp_async_wait<0>();
+    __syncthreads();
+    PS_CLOCK(3);
+    if (blockIdx.x == 0) {
+        // the factored diagonal block goes back to W (L11 strictly below, U11 on and above the diagonal)
+        for (int e = tid; e < NB * NB; e += 128) {
+            const int rr = e / NB, cc = e % NB;
+            if (rr < jb && cc < jb) W[(size_t)(k0 + rr) * ld + k0 + cc] = sD[rr * PS_LD + cc];
+        }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double acc_re[2][4][2], acc_im[2][4][2];
 #pragma unroll
-                    for (int k = c + 1; k < NB; ++k) zfms(row[k], l, sD[c][k]);
-                }
-                if (i == c + 1) {
-                    // the next pivot row is complete: publish it
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int k = 0; k < NB; ++k) sD[i][k] = row[k];
+        for (int j = 0; j < 4; ++j) {
+            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
+            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+        }
+    if (row_role) {
+        // T (64 x 32) = tile (64 x 32) * Mi^T: warp w owns rows 16w .. 16w+15
+#pragma unroll 2
+        for (int k4 = 0; k4 < NB; k4 += 4) {
+            z_t af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = sT[(warp * 16 + i * 8 + g) * PS_LD + k4 + q];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = sM[(j * 8 + g) * PS_LD + k4 + q];    // B[k][n] = Mi[n][k]
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double nai = -af[i].y;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma(acc_re[i][j], af[i].x, bf[j].x);
+                    dmma(acc_im[i][j], af[i].x, bf[j].y);
+                    dmma(acc_re[i][j], nai, bf[j].y);
+                    dmma(acc_im[i][j], af[i].y, bf[j].x);
                 }
-                __syncwarp();
             }
         }
-        // rows > publish point already stored when they became pivot rows; row 0 never changed
-    }
-    __syncthreads();
-    if ((int)blockIdx.x < n_row_ctas) {
-        const int r = blockIdx.x * TPB + threadIdx.x;      // row offset below k0
-        if (r < dim - k0) {
-            z_t* myrow = W + (size_t)(k0 + r) * ld + k0;
-            if (r < jb) {
-                // rows of the diagonal block: CTA 0 writes the factored block back
-                if (blockIdx.x == 0) {
-                    for (int c = 0; c < jb; ++c) myrow[c] = sD[r][c];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = r0 + warp * 16 + i * 8 + g;
+            if (k0 + r >= dim) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = j * 8 + 2 * q + e;
+                    if (c >= jb) continue;
+                    const z_t t = make_double2(acc_re[i][j][e], acc_im[i][j][e]);
+                    if (fabs(t.x) + fabs(t.y) > tau * sAbs[c]) bad = 1;
+                    W[(size_t)(k0 + r) * ld + k0 + c] = zmul(t, sInv[c]);
+                    W[(size_t)(k0 + c) * ld + k0 + r] = t;
                 }
-            } else {
-                z_t a[NB];
-#pragma unroll
-                for (int k = 0; k < NB; ++k) a[k] = k < jb ? myrow[k] : make_double2(0., 0.);
-#pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    if (c < jb) {
-                        if (fabs(a[c].x) + fabs(a[c].y) > tau * sAbs[c]) bad = 1;
-                        const z_t l = zmul(a[c], sInv[c]);
-                        a[c] = l;
-#pragma unroll
-                        for (int k = c + 1; k < NB; ++k) zfms(a[k], l, sD[c][k]);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NB; ++k)
-                    if (k < jb) myrow[k] = a[k];
-                // U[k0+c, k0+r] = l_rc * u_cc: coalesced across the threads of a warp
-                z_t* ucol = W + (size_t)k0 * ld + k0 + r;
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < jb) ucol[(size_t)c * ld] = zmul(a[c], sD[c][c]);
             }
         }
     } else {
-        const int col = ((int)blockIdx.x - n_row_ctas) * TPB + threadIdx.x;
-        if (col < ycols) {
-            z_t* M = Y + col;
-            z_t x[NB];
+        // rows k0..ke of Y (32 x 64 tile) <- Mi * tile: warp w owns rows 16 (w&1).., columns 32 (w>>1)..
+        const int mb = warp & 1, nh = warp >> 1;
+#pragma unroll 2
+        for (int k4 = 0; k4 < NB; k4 += 4) {
+            z_t af[2], bf[4];
 #pragma unroll
-            for (int rr = 0; rr < NB; ++rr) x[rr] = rr < jb ? M[(size_t)(k0 + rr) * ld] : make_double2(0., 0.);
+            for (int i = 0; i < 2; ++i) af[i] = sM[(mb * 16 + i * 8 + g) * PS_LD + k4 + q];
 #pragma unroll
-            for (int rr = 1; rr < NB; ++rr) {
+            for (int j = 0; j < 4; ++j) bf[j] = sT[(k4 + q) * PS_LDY + nh * 32 + j * 8 + g];
 #pragma unroll
-                for (int cc = 0; cc < rr; ++cc) zfms(x[rr], sD[rr][cc], x[cc]);
+            for (int i = 0; i < 2; ++i) {
+                const double nai = -af[i].y;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma(acc_re[i][j], af[i].x, bf[j].x);
+                    dmma(acc_im[i][j], af[i].x, bf[j].y);
+                    dmma(acc_re[i][j], nai, bf[j].y);
+                    dmma(acc_im[i][j], af[i].y, bf[j].x);
+                }
             }
+        }
 #pragma unroll
-            for (int rr = 0; rr < NB; ++rr)
-                if (rr < jb) M[(size_t)(k0 + rr) * ld] = x[rr];
+        for (int i = 0; i < 2; ++i) {
+            const int m = mb * 16 + i * 8 + g;
+            if (m >= jb) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = c0 + nh * 32 + j * 8 + 2 * q + e;
+                    if (n >= ycols) continue;
+                    Y[(size_t)(k0 + m) * ld + n] = make_double2(acc_re[i][j][e], acc_im[i][j][e]);
+                }
+            }
         }
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+    PS_CLOCK(4);
+    if (__syncthreads_or(bad) && tid == 0) atomicOr(flag, 1);
 }
 
 // Trailing update of the symmetric path in ONE launch: C1 -= A*B1 on the LOWER block triangle only
@@ -841,20 +956,27 @@ transpose_invd_kernel(const z_t* __restrict__ Y, const z_t* __restrict__ W, z_t*
     }
 }
 
-// partial[t] = sum over tile t = (I, J), I >= J, of P_ij * (I > J ? B_ij + B_ji : B_ji) with
+// partial[chunk][t] = sum over tile t = (I, J), I >= J, of P_ij * (I > J ? B_ij + B_ji : B_ji) with
 // P = YT * Y = A^-1 (only k >= 64 I contributes: YT is upper, Y lower triangular).
 __global__ void __launch_bounds__(256, 2)
 ptrace_kernel(const z_t* __restrict__ YT, const z_t* __restrict__ Y, const z_t* __restrict__ Bd, int dim,
-              z_t* __restrict__ partial) {
+              int ck, z_t* __restrict__ partial) {
     __shared__ double red[2][8];
     const int t = blockIdx.x;
     int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
     while ((I + 1) * (I + 2) / 2 <= t) ++I;
     while (I * (I + 1) / 2 > t) --I;
     const int J = t - I * (I + 1) / 2;
-    const int kstart = I * GM;
+    // split K: chunk blockIdx.y of the range [64 I, dim) (small systems have too few tiles to fill
+    // the GPU, and the longest tile would be the critical path)
+    const int kstart = I * GM + (int)blockIdx.y * ck;
+    const int kend = blockIdx.y + 1 == gridDim.y ? dim : (kstart + ck < dim ? kstart + ck : dim);
+    if (kstart >= dim) {
+        if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + t] = make_double2(0., 0.);
+        return;
+    }
     GemmAcc acc;
-    zgemm_mainloop(acc, YT + kstart, dim, Y + (size_t)kstart * dim, dim, dim, dim, dim - kstart, I * GM,
+    zgemm_mainloop(acc, YT + kstart, dim, Y + (size_t)kstart * dim, dim, dim, dim, kend - kstart, I * GM,
                    J * GN);
     double sr = 0., si = 0.;
 #pragma unroll
@@ -890,7 +1012,7 @@ ptrace_kernel(const z_t* __restrict__ YT, const z_t* __restrict__ Y, const z_t* 
     if (threadIdx.x == 0) {
         double x = 0., y = 0.;
         for (int w = 0; w < 8; ++w) { x += red[0][w]; y += red[1][w]; }
-        partial[t] = make_double2(x, y);
+        partial[(size_t)blockIdx.y * gridDim.x + t] = make_double2(x, y);
     }
 }
 
@@ -927,6 +1049,8 @@ static cudaError_t gemm_setup() {
                              (int)G_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ptrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(panel_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
@@ -1242,7 +1366,7 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
 // ------------------------------------------------------------------ symmetric path: driver
 size_t dense_sym_workspace_bytes(int dim) {
     const size_t nt = (dim + GM - 1) / GM;
-    return sizeof(z_t) * (nt * (nt + 1) / 2) + 64;
+    return sizeof(z_t) * (nt * (nt + 1) / 2) * PTRACE_MAX_CHUNKS + 64;
 }
 
 // W <- A (lower block triangle) + bitwise symmetry check (raises bit 2 of *d_flag).  Kept apart
@@ -1296,9 +1420,9 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
         for (int k0 = K0; k0 < KE; k0 += NB) {
             const int jb = KE - k0 < NB ? KE - k0 : NB;
             const int ke = k0 + jb;
-            const int n_row = (dim - k0 + 127) / 128, n_col = (ke + 127) / 128;
-            panel_sym_kernel<128><<<n_row + n_col, 128, 0, stream>>>(W, Y, ld, dim, k0, jb, ke, n_row, g_tau,
-                                                                     d_flag, d_info);
+            const int n_row = (dim - ke + PS_ROWS - 1) / PS_ROWS, n_col = (ke + PS_ROWS - 1) / PS_ROWS;
+            panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, ke, n_row,
+                                                                            g_tau, d_flag, d_info);
             ++nl;
             // inside the outer block: columns [ke, KE) of W below the panel, rows [ke, KE) of Y
             if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, ke, k0, jb);
@@ -1313,9 +1437,16 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
         ++nl;
         const int nt = (dim + GM - 1) / GM;
         const int ntiles = nt * (nt + 1) / 2;
-        ptrace_kernel<<<ntiles, 256, G_SMEM_BYTES, stream>>>(YT, Y, (const z_t*)Bv, dim, (z_t*)sym_workspace);
+        int nchunks = (600 + ntiles - 1) / ntiles;
+        if (nchunks > PTRACE_MAX_CHUNKS) nchunks = PTRACE_MAX_CHUNKS;
+        if (nchunks > (dim + 127) / 128) nchunks = (dim + 127) / 128;
+        if (nchunks < 1) nchunks = 1;
+        const int ck = (((dim + nchunks - 1) / nchunks) + GK - 1) / GK * GK;
+        ptrace_kernel<<<dim3(ntiles, nchunks), 256, G_SMEM_BYTES, stream>>>(YT, Y, (const z_t*)Bv, dim, ck,
+                                                                            (z_t*)sym_workspace);
         ++nl;
-        reduce_partials_kernel<<<1, 256, 0, stream>>>((const z_t*)sym_workspace, ntiles, (z_t*)d_trace);
+        reduce_partials_kernel<<<1, 256, 0, stream>>>((const z_t*)sym_workspace, ntiles * nchunks,
+                                                      (z_t*)d_trace);
         ++nl;
     }
     if (n_launches) *n_launches += nl;
