@@ -65,7 +65,7 @@ struct emme_solver {
     int peer_count = 0;               // 0: local stores only
     emme_stats stats{};
     unsigned long long launches = 0;
-    int refill_min = 16;
+    int refill_min = 32;
     int optimistic = 1;               // try the interchange-free factorisation first
     int null_optimistic = 1;
     int use_graph = 1;                // replay the optimistic dense step as a CUDA graph

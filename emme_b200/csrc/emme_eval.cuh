@@ -147,22 +147,52 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     const int n0 = (int)(floor(az) + 1.0);
     int n = n0;
     double dn = (double)n0;
-    // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared:
-    // max(T*n*|2/z|, T^2).  The first term only wins for |z| < n*1e-7, so |2/z| = 2/|z| is formed
-    // only then.
-    double thr2 = THRESHOLD * THRESHOLD;
-    if (az < 1e-5) thr2 = fmax(THRESHOLD * (dn * (2.0 / az)), thr2);
-    // forward recurrence p_{k+1} = p_{k-1} - (2n/z) p_k, two trips per round (no register moves)
-    cplx pa = mk(0., 0.), pb = mk(1., 0.);   // pa = p_{k-1}, pb = p_k
-    for (;;) {
-        if (!le_nonneg(norm2(pb), thr2)) break;
-        pa = cfms(dn * zc, pb, pa);          // pa <- p_{k+1}
-        dn += 1.0;
-        ++n;
-        if (!le_nonneg(norm2(pa), thr2)) break;
-        pb = cfms(dn * zc, pa, pb);          // pb <- p_{k+2}
-        dn += 1.0;
-        ++n;
+    // Forward recurrence p_{k+1} = p_{k-1} - (2n/z) p_k until |p|^2 exceeds the threshold.  Only the
+    // STOPPING INDEX N is used below (the backward pass restarts from y_N = 1), and the result does
+    // not depend on it beyond 1/|p_N|^2 ~ 2.5e-15: the search therefore runs in FP32 on the
+    // otherwise idle FP32 pipe (relative error ~1e-6 in |p|^2 can move N by one only when |p_N|^2
+    // sits within 1e-6 of the threshold).  Two trips per round, no register moves.  (A speculative
+    // four-trips-per-round variant that takes the tests off the critical path measured no faster.)
+    if (az >= 1e-5) {
+        const float thr2 = (float)(THRESHOLD * THRESHOLD);
+        const float zr = (float)zc.re, zi = (float)zc.im;
+        float fn = (float)n0;
+        float par = 0.f, pai = 0.f, pbr = 1.f, pbi = 0.f;   // pa = p_{k-1}, pb = p_k
+        for (;;) {
+            if (!(fmaf(pbr, pbr, pbi * pbi) <= thr2)) break;
+            {
+                const float cr = fn * zr, ci = fn * zi;
+                par = fmaf(-cr, pbr, fmaf(ci, pbi, par));     // pa <- p_{k+1}
+                pai = fmaf(-cr, pbi, fmaf(-ci, pbr, pai));
+            }
+            fn += 1.0f;
+            ++n;
+            if (!(fmaf(par, par, pai * pai) <= thr2)) break;
+            {
+                const float cr = fn * zr, ci = fn * zi;
+                pbr = fmaf(-cr, par, fmaf(ci, pai, pbr));     // pb <- p_{k+2}
+                pbi = fmaf(-cr, pai, fmaf(-ci, par, pbi));
+            }
+            fn += 1.0f;
+            ++n;
+        }
+        dn = (double)n;
+    } else {
+        // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared:
+        // max(T*n*|2/z|, T^2).  The first term only wins for |z| < n*1e-7 (FP64 here: rare, and the
+        // products overflow FP32).
+        const double thr2 = fmax(THRESHOLD * (dn * (2.0 / az)), THRESHOLD * THRESHOLD);
+        cplx pa = mk(0., 0.), pb = mk(1., 0.);   // pa = p_{k-1}, pb = p_k
+        for (;;) {
+            if (!le_nonneg(norm2(pb), thr2)) break;
+            pa = cfms(dn * zc, pb, pa);          // pa <- p_{k+1}
+            dn += 1.0;
+            ++n;
+            if (!le_nonneg(norm2(pa), thr2)) break;
+            pb = cfms(dn * zc, pa, pb);          // pb <- p_{k+2}
+            dn += 1.0;
+            ++n;
+        }
     }
     cnt.fwd += (unsigned)(n - n0);
     --n;
@@ -217,6 +247,83 @@ EMME_HD NodeTrig node_trig(double x) {
     return n;
 }
 
+// exp(a + i b) for the integrand's exponential factor: a is known to lie in [-40, ~60] (the
+// underflow guard has already removed a < -40), so the general-purpose exp()/sincos() of the CUDA
+// math library -- 48 + 74 instructions per call, two thirds of them range/special-case handling on
+// the integer pipe -- are replaced by straight-line code: Cody-Waite reduction with FMAs, fdlibm's
+// minimax kernels for sin/cos on [-pi/4, pi/4] (error < 2^-58) and a degree-13 Taylor kernel for
+// exp on [-ln2/2, ln2/2] (truncation 4e-18).  |b| >= 2^19 (never seen in practice) and a outside
+// [-700, 700] fall back to the library.  tests/test_emul.py::test_lean_cexp pins the product to <= 3 ulp per component.
+// Measured on B200 (N = 8192): 122.2 ms with it, 121.0 ms with the library calls -- the kernel is
+// not issue bound, so it is OFF by default and kept as a tested alternative.
+#ifndef EMME_LEAN_CEXP
+#define EMME_LEAN_CEXP 0
+#endif
+
+EMME_HD double two_to(int k) {          // 2^k for -1022 <= k <= 1023
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((k + 1023) << 20, 0);
+#else
+    return ldexp(1.0, k);
+#endif
+}
+
+EMME_HD cplx cexp_lib(double a, double b) {
+    double es, ec;
+    sincos(b, &es, &ec);
+    const double er = exp(a);
+    return mk(er * ec, er * es);
+}
+
+EMME_HD cplx cexp_lean(double a, double b) {
+    if (fabs(b) < 524288.0 && fabs(a) < 700.0) {
+        const double MAGIC = 6755399441055744.0;       // 1.5 * 2^52: round-to-nearest-integer trick
+        // ---- sin b, cos b ----
+        const double qd = fma(b, 6.36619772367581382433e-01, MAGIC) - MAGIC;
+        double r = fma(-qd, 1.57079632673412561417e+00, b);       // pi/2, first 33 bits (exact product)
+        r = fma(-qd, 6.07710050630396597660e-11, r);              // next 33 bits
+        r = fma(-qd, 2.02226624879595063154e-21, r);              // tail
+        const double z = r * r;
+        double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+        ps = fma(z, ps, 2.75573137070700676789e-06);
+        ps = fma(z, ps, -1.98412698298579493134e-04);
+        ps = fma(z, ps, 8.33333333332248946124e-03);
+        ps = fma(z, ps, -1.66666666666666324348e-01);
+        const double sn = fma(z * r, ps, r);
+        double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+        pc = fma(z, pc, -2.75573143513906633035e-07);
+        pc = fma(z, pc, 2.48015872894767294178e-05);
+        pc = fma(z, pc, -1.38888888888741095749e-03);
+        pc = fma(z, pc, 4.16666666666666019037e-02);
+        const double hz = 0.5 * z, w = 1.0 - hz;
+        const double cs = w + (((1.0 - w) - hz) + z * (z * pc));
+        const int q = (int)qd;
+        double s_ = (q & 1) ? cs : sn, c_ = (q & 1) ? sn : cs;
+        if (q & 2) s_ = -s_;
+        if ((q + 1) & 2) c_ = -c_;
+        // ---- exp a ----
+        const double kd = fma(a, 1.44269504088896338700e+00, MAGIC) - MAGIC;
+        double t = fma(-kd, 6.93147180369123816490e-01, a);       // ln2, first 33 bits
+        t = fma(-kd, 1.90821492927058770002e-10, t);
+        double pe = fma(t, 1.6059043836821613e-10, 2.08767569878681e-09);   // 1/13!, 1/12!
+        pe = fma(t, pe, 2.505210838544172e-08);
+        pe = fma(t, pe, 2.755731922398589e-07);
+        pe = fma(t, pe, 2.7557319223985893e-06);
+        pe = fma(t, pe, 2.48015873015873e-05);
+        pe = fma(t, pe, 1.984126984126984e-04);
+        pe = fma(t, pe, 1.388888888888889e-03);
+        pe = fma(t, pe, 8.333333333333333e-03);
+        pe = fma(t, pe, 4.1666666666666664e-02);
+        pe = fma(t, pe, 1.6666666666666666e-01);
+        pe = fma(t, pe, 0.5);
+        pe = fma(t, pe, 1.0);
+        pe = fma(t, pe, 1.0);
+        const double er = pe * two_to((int)kd);
+        return mk(er * c_, er * s_);
+    }
+    return cexp_lib(a, b);
+}
+
 // g(x) for mode m (0, 1, 2) at the node described by nt.
 EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, const NodeTrig& nt,
                        EvalCounters& cnt) {
@@ -257,10 +364,11 @@ EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, const Nod
                     rc.wsi_etai * (mk(pc.hb, 0.) - lambda) * il3;
     const cplx i1 = pc.c1 * il3;
 
-    double es, ec;
-    sincos(arg.im, &es, &ec);
-    const double er = exp(arg.re);
-    const cplx se = mk(er * ec, er * es);
+#if EMME_LEAN_CEXP
+    const cplx se = cexp_lean(arg.re, arg.im);
+#else
+    const cplx se = cexp_lib(arg.re, arg.im);
+#endif
 
     cplx pw = itaut;                           // nu^m / tau~        (:174)
     if (m >= 1) pw = pw * nu;

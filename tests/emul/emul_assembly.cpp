@@ -151,3 +151,12 @@ extern "C" int emul_assemble(const emme_params* p, int N, const double* eta, con
     }
     return 0;
 }
+
+// exp(a + i b) through the kernel's own cexp_lean (emme_eval.cuh), for the ulp test
+extern "C" void emul_cexp(const double* a, const double* b, int n, double* out) {
+    for (int i = 0; i < n; ++i) {
+        const cplx v = cexp_lean(a[i], b[i]);
+        out[2 * i] = v.re;
+        out[2 * i + 1] = v.im;
+    }
+}
