@@ -57,6 +57,11 @@ def algorithmic_flops(st):
     return st["evals"] * FLOP_FIXED + FLOP_TRIP * (st["fwd_trips"] + st["bwd_trips"])
 
 
+def fp64_flops(st):
+    """The same count without the Miller forward trips: the kernel runs that search in FP32."""
+    return st["evals"] * FLOP_FIXED + FLOP_TRIP * st["bwd_trips"]
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -178,6 +183,7 @@ def timed_iterates(solver, inp, omega0, steps, tol, reseed_points, e2e=None):
         st = solver.stats()
         out["assemblies"] += 1
         out["flops"] += algorithmic_flops(st)
+        out["flops_fp64"] = out.get("flops_fp64", 0.0) + fp64_flops(st)
         out["asm_ms"] += st["assemble_ms"]
         out["dense_ms"] += st["dense_ms"]
         out["dense_flops"] += st["dense_flops"]       # flops of the path that ran (4 dim^3 symmetric, 26/3 dim^3 LU)
@@ -412,6 +418,12 @@ def bench_b200(args, rank, local_rank, world):
                                         "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 FMA/clk x 2 x "
                                         f"{nominal_mhz.value:.0f} MHz = {148 * 64 * 2 * nominal_mhz.value / 1e6:.1f}",
                          "flops_per_launch": run["flops"] / args.steps,
+                         "achieved_fp64_only": run["flops_fp64"] / (run["asm_ms"] * 1e-3) / 1e12,
+                         "frac_fp64_only": (run["flops_fp64"] / (run["asm_ms"] * 1e-3) / 1e12 / peak_tf.value
+                                            if peak_tf.value else None),
+                         "note": "achieved = SURVEY 8d algorithmic flops (354/eval + 14 per Miller trip) / launch "
+                                 "time; the forward (start-index) trips execute in FP32, achieved_fp64_only "
+                                 "leaves them out",
                          "avg_launch_ms": run["asm_ms"] / args.steps,
                          "hbm_achieved_gbs": 16.0 * dim * dim / (run["asm_ms"] / args.steps * 1e-3) / 1e9,
                          "hbm_peak_gbs": hbm_peak, "traffic": traffic,

@@ -17,6 +17,7 @@
 #include "../host/parameters.hpp"
 #include "assembly.h"
 #include "dense.h"
+#include "qr.h"
 #include "run_const.h"
 
 using emme::RunConst;
@@ -52,6 +53,8 @@ struct emme_solver {
     void* d_dense_ws = nullptr;
     // symmetric dense path: M = L^-1, its scaled transpose, per-tile partial traces
     void *Y = nullptr, *YT = nullptr, *d_sym_ws = nullptr;
+    void* d_qr_ws = nullptr;          // QR-secant iterate: norms, reflector scalars, vectors
+    double2* d_qr_out = nullptr;      // [R_nn, (Q^H A' v)_n]
     double2* d_trace = nullptr;
     int* d_info = nullptr;
     // Newton state
@@ -152,6 +155,8 @@ int emme_destroy(emme_solver* s) {
     cudaFree(s->Y);
     cudaFree(s->YT);
     cudaFree(s->d_sym_ws);
+    cudaFree(s->d_qr_ws);
+    cudaFree(s->d_qr_out);
     cudaFree(s->d_trace);
     cudaFree(s->d_info);
     cudaFree(s->d_flag);
@@ -570,6 +575,75 @@ int emme_newton_trace_step(emme_solver* s, double* wr, double* wi, double* dr, d
     int rc = emme_step_begin(s);
     if (rc) return rc;
     return emme_step_finish(s, wr, wi, dr, di);
+}
+
+// newtonQRSecantIteration (include/solver.h:210-383): W <- A, Householder QR with column
+// pivoting, null-vector estimate v from R, delta = -R_nn / (Q^H A' v)_n.  A and A' are only read.
+static int qr_delta(emme_solver* s, zc* delta) {
+    if (!s->d_qr_ws) CU(cudaMalloc(&s->d_qr_ws, emme::qr_workspace_bytes(s->dim)));
+    if (!s->d_qr_out) CU(cudaMalloc(&s->d_qr_out, 2 * sizeof(double2)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, s->stream));
+    CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
+    CU(emme::launch_qr_step(s->W, s->Ad, s->dim, s->d_qr_ws, s->d_qr_out, s->d_info, s->stream,
+                            &s->launches));
+    CU(cudaEventRecord(e1, s->stream));
+    double out[4];
+    int info = 0;
+    CU(cudaMemcpyAsync(out, s->d_qr_out, sizeof out, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&info, s->d_info, sizeof info, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    s->stats.dense_ms = ms;
+    s->stats.dense_flops = (16.0 / 3.0) * (double)s->dim * s->dim * s->dim;   // Householder QR, complex
+    if (info != 0) {
+        // the reference's message for ztrtrs info > 0 (include/solver.h:312-314)
+        return fail(info, "\xe7\x9f\xa9\xe9\x98\xb5\xe7\xac\xac " + std::to_string(info) +
+                              " \xe4\xb8\xaa\xe5\xaf\xb9\xe8\xa7\x92\xe7\xba\xbf\xe5\x85\x83\xe7\xb4\xa0\xe4\xb8\xba\xe9\x9b\xb6\xef\xbc\x8c"
+                              "\xe6\x97\xa0\xe6\xb3\x95\xe6\xb1\x82\xe8\xa7\xa3 (R has a zero diagonal element: cannot solve)");
+    }
+    *delta = -zc(out[0], out[1]) / zc(out[2], out[3]);   // :370
+    return 0;
+}
+
+int emme_qr_step_begin(emme_solver* s) {
+    if (!s) return fail(-1, "null handle");
+    if (!s->seeded) return fail(EMME_E_STATE, "emme_newton_qr_step before emme_seed");
+    CU(cudaSetDevice(s->device));
+    zc delta;
+    int rc = qr_delta(s, &delta);
+    if (rc) return rc;
+    s->dw = delta;
+    s->w += delta;               // :371
+    std::swap(s->A, s->Aold);    // eigen_matrix_old = eigen_matrix (:211) without a copy
+    return assemble_current(s);  // :380
+}
+
+int emme_newton_qr_step(emme_solver* s, double* wr, double* wi, double* dr, double* di) {
+    int rc = emme_qr_step_begin(s);
+    if (rc) return rc;
+    return emme_step_finish(s, wr, wi, dr, di);   // :382
+}
+
+int emme_qr_delta(emme_solver* s, const void* host_A, const void* host_Ad, double* dr, double* di) {
+    if (!s) return fail(-1, "null handle");
+    if (!host_A) return fail(-2, "null A");
+    if (!host_Ad) return fail(-3, "null Ad");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_newton_buffers(s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->A, host_A, s->bytes(), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->Ad, host_Ad, s->bytes(), cudaMemcpyHostToDevice, s->stream));
+    zc delta;
+    rc = qr_delta(s, &delta);
+    if (dr) *dr = delta.real();
+    if (di) *di = delta.imag();
+    return rc;
 }
 
 int emme_get_eigen_value(const emme_solver* s, double* wr, double* wi, double* dr, double* di) {

@@ -46,6 +46,17 @@ void EigenSolver::newtonTraceSecantIteration() {
     check(rc);
 }
 
+void EigenSolver::newtonQRSecantIteration() {
+    double wr, wi, dr, di;
+    const int rc = emme_newton_qr_step(h_, &wr, &wi, &dr, &di);
+    double a, b, c, d;
+    if (emme_get_eigen_value(h_, &a, &b, &c, &d) == 0) {
+        eigen_value = {a, b};
+        d_eigen_value = {c, d};
+    }
+    check(rc);
+}
+
 std::vector<EigenSolver::value_type> EigenSolver::nullSpace() {
     std::vector<value_type> v(dim);
     check(emme_null_space(h_, v.data()));

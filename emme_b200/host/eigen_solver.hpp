@@ -53,6 +53,7 @@ class EigenSolver {
 
     void matrixAssembler(matrix_type& mat);   // A(eigen_value) into a host matrix
     void newtonTraceSecantIteration();        // include/solver.h:113-160
+    void newtonQRSecantIteration();           // include/solver.h:210-383
     std::vector<value_type> nullSpace();      // include/solver.h:58-112 (inverse iteration)
     const matrix_type& eigen_matrix();        // downloads the current A
 

@@ -8,7 +8,7 @@
 // Scan objects {head, step, tail} follow the reference's generator and its continuation of omega
 // between scan points (src/main.cpp:139-172,262-325); a failing point is recorded as
 // {"eigenvalue": "NaN", "reason": ...} and the scan continues (src/main.cpp:300-318).
-// Only method "eigen" with iteration_method "TraceSecant" is implemented;
+// Only method "eigen" is implemented, with both iteration methods;
 // anything else raises the reference's "not supported" error text.
 #include <array>
 #include <chrono>
@@ -69,12 +69,13 @@ Value solve_once_eigen(const Value& input, std::complex<double>& omega_initial_g
     emme::EigenSolver solver(*para, omega_initial_guess);
     timers.end("initial");
     const std::string iter_method = input.at("iteration_method").as_string();
-    if (iter_method != "TraceSecant")
-        throw std::runtime_error("iteration_method '" + iter_method +
-                                 "' is not supported by emme_b200 (TraceSecant only).");
     for (int j = 0; j <= para->iteration_step_limit; j++) {
         timers.begin("Iteration");
-        solver.newtonTraceSecantIteration();
+        if (iter_method == "TraceSecant") {   // src/main.cpp:45-49
+            solver.newtonTraceSecantIteration();
+        } else {
+            solver.newtonQRSecantIteration();
+        }
         timers.end("Iteration");
         std::cout << "        " << solver.eigen_value << '\n';
         if (std::abs(solver.d_eigen_value) < std::abs(tol * solver.eigen_value)) break;

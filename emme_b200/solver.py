@@ -137,6 +137,22 @@ class EigenSolver:
         self._pull()
         capi.check(rc)
 
+    def newtonQRSecantIteration(self):
+        """EigenSolver::newtonQRSecantIteration (include/solver.h:210-383)."""
+        v = [C.c_double() for _ in range(4)]
+        rc = self._lib.emme_newton_qr_step(self._h, *[C.byref(x) for x in v])
+        self._pull()
+        capi.check(rc)
+
+    def qr_delta(self, A, Ad):
+        """delta = -R_nn/(Q^H Ad v)_n of the QR-secant iterate for host matrices (dense step only)."""
+        A = np.ascontiguousarray(A, dtype=np.complex128)
+        Ad = np.ascontiguousarray(Ad, dtype=np.complex128)
+        dr, di = C.c_double(), C.c_double()
+        capi.check(self._lib.emme_qr_delta(self._h, A.ctypes.data, Ad.ctypes.data,
+                                           C.byref(dr), C.byref(di)))
+        return complex(dr.value, di.value)
+
     def trace_delta(self, A, Ad):
         """delta = -1/trace(A^-1 Ad) for host matrices (dense step only)."""
         A = np.ascontiguousarray(A, dtype=np.complex128)
@@ -191,18 +207,20 @@ class EigenSolver:
 
 def solve_once_eigen(inp, omega0, device=0, on_iterate=None, solver=None):
     """The loop of solve_once_eigen (src/main.cpp:19-57): seed, then at most
-    iteration_step_limit+1 TraceSecant iterates, stopping when |delta| < tol*|omega|.
-    Returns (omega, iterates, solver)."""
+    iteration_step_limit+1 iterates -- newtonTraceSecantIteration when iteration_method is
+    "TraceSecant", newtonQRSecantIteration otherwise (src/main.cpp:45-49) -- stopping when
+    |delta| < tol*|omega|.  Returns (omega, iterates, solver)."""
     tol = inp.number("iteration_precision")
     limit = int(inp.number("iteration_step_limit"))
     method = inp.string("iteration_method")
-    if method != "TraceSecant":
-        raise NotImplementedError("iteration_method other than TraceSecant (SURVEY.md row N2)")
     s = solver or EigenSolver.from_input(inp, device=device)
     s.seed(omega0)
     iterates = []
     for _ in range(limit + 1):
-        s.newtonTraceSecantIteration()
+        if method == "TraceSecant":
+            s.newtonTraceSecantIteration()
+        else:
+            s.newtonQRSecantIteration()
         iterates.append((s.eigen_value, s.d_eigen_value))
         if on_iterate:
             on_iterate(s)

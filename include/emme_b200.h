@@ -113,6 +113,15 @@ int emme_assemble_device(emme_solver* s, double wr, double wi, void* dev_out, in
  *   delta = -1/trace(A^-1 Ad). */
 int emme_seed(emme_solver* s, double w0r, double w0i);
 int emme_newton_trace_step(emme_solver* s, double* wr, double* wi, double* dr, double* di);
+/* emme_newton_qr_step: newtonQRSecantIteration (include/solver.h:210-383), the iterate of
+ *   iteration_method != "TraceSecant" (src/main.cpp:45-49): Householder QR with column pivoting
+ *   A P = Q R (zgeqp3), x = R[0:n-1,0:n-1]^-1 R[0:n-1,n-1] (ztrtrs), v[jpvt[i]] = -x[i],
+ *   v[jpvt[n-1]] = 1, delta = -R[n-1][n-1] / (Q^H A' v)[n-1] (zunmqr), omega += delta,
+ *   re-assemble, A' = (A - A_old)/delta.  Returns k > 0 if R[k-1][k-1] is exactly zero (the
+ *   reference's ztrtrs runtime_error, include/solver.h:308-316).
+ * emme_qr_delta: only the dense part on caller-provided HOST matrices (for tests). */
+int emme_newton_qr_step(emme_solver* s, double* wr, double* wi, double* dr, double* di);
+int emme_qr_delta(emme_solver* s, const void* host_A, const void* host_Ad, double* dr, double* di);
 int emme_get_eigen_value(const emme_solver* s, double* wr, double* wi, double* dr, double* di);
 int emme_trace_delta(emme_solver* s, const void* host_A, const void* host_Ad, double* dr,
                      double* di);
@@ -126,6 +135,7 @@ int emme_seed_begin(emme_solver* s, double w0r, double w0i);   /* assemble shard
 int emme_seed_middle(emme_solver* s);                          /* A_old<-A, omega+=delta, assemble shard */
 int emme_seed_finish(emme_solver* s);                          /* A' = (A-A_old)/delta */
 int emme_step_begin(emme_solver* s);                           /* dense step, omega+=delta, assemble shard */
+int emme_qr_step_begin(emme_solver* s);                        /* same for the QR-secant iterate */
 int emme_step_finish(emme_solver* s, double* wr, double* wi, double* dr, double* di);
 void* emme_matrix_device_ptr(emme_solver* s, int which);
 /* Fused exchange (no collective): export the CUDA IPC handles (64 bytes each) of the two physical

@@ -104,9 +104,30 @@ def rounding_floor():
     (HERE / "rounding_floor.json").write_text(json.dumps(out, indent=1))
 
 
+NEWTON_QR = ["c1_n64", "c1_n128", "c1_gk31_n128", "c1_em_n64", "c1_pos_n64"]
+
+
+def newton_qr():
+    """Iterate lists of the reference's OTHER iteration_method (newtonQRSecantIteration,
+    include/solver.h:210-383): the same inputs with "iteration_method": "QRSecant"."""
+    gpath = HERE / "golden.json"
+    G = json.loads(gpath.read_text())
+    G["newton_qr"] = {}
+    with tempfile.TemporaryDirectory() as td:
+        for case in NEWTON_QR:
+            txt = (HERE / "inputs" / f"{case}.json").read_text()
+            assert '"TraceSecant"' in txt
+            Path(f"{td}/in.json").write_text(txt.replace('"TraceSecant"', '"QRSecant"'))
+            G["newton_qr"][case] = parse_newton(run("newton", f"{td}/in.json"))
+            print(case, "newton_qr", G["newton_qr"][case]["final"])
+    gpath.write_text(json.dumps(G, indent=1))
+
+
 def main():
     if "--floor" in sys.argv:
         return rounding_floor()
+    if "--qr" in sys.argv:
+        return newton_qr()
     full = "--full" in sys.argv
     gpath = HERE / "golden.json"
     G = json.loads(gpath.read_text()) if gpath.exists() else {}

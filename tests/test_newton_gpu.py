@@ -166,6 +166,74 @@ def test_newton_iterates_match_reference(case, golden, native_lib):
     assert abs(w - rf) <= 1e-8 * abs(rf)
 
 
+def _qr_delta_lapack(A, Ad):
+    """newtonQRSecantIteration's formula (include/solver.h:246-370) with LAPACK itself: scipy's
+    qr(pivoting=True) is zgeqp3."""
+    import scipy.linalg as sl
+    n = A.shape[0]
+    Q, R, piv = sl.qr(A, pivoting=True)
+    x = sl.solve_triangular(R[:n - 1, :n - 1], R[:n - 1, n - 1])
+    v = np.zeros(n, dtype=np.complex128)
+    v[piv[:n - 1]] = -x
+    v[piv[n - 1]] = 1.0
+    t = Q.conj().T @ (Ad @ v)
+    return -R[n - 1, n - 1] / t[n - 1], int(piv[n - 1])
+
+
+@pytest.mark.parametrize("dim", [2, 3, 17, 64, 100, 129, 300])
+def test_qr_delta_matches_lapack(dim, native_lib):
+    """The QR-secant dense step on random complex matrices with well separated column norms
+    (so that the pivot order is not decided by rounding) against LAPACK's zgeqp3 path."""
+    rng = np.random.default_rng(40 + dim)
+    A = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    A *= rng.uniform(0.2, 5.0, dim)[None, :]
+    B = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    s = _trace_solver(dim)
+    d = s.qr_delta(A, B)
+    ref, _ = _qr_delta_lapack(A, B)
+    assert abs(d - ref) <= 1e-10 * abs(ref), (d, ref)
+
+
+def test_qr_delta_on_real_matrices(golden, native_lib):
+    """Same, on an EMME matrix pair (all column norms within a few per cent of each other)."""
+    inp = Input(cases.input_path("c1_n128"))
+    s = EigenSolver.from_input(inp)
+    A = cases.ref_matrix("c1_n128")
+    A2 = s.matrixAssembler(-0.79 + 0.251j).copy()
+    Ad = (A - A2) / (0.01 - 0.001j)
+    d = s.qr_delta(A, Ad)
+    ref, last = _qr_delta_lapack(A, Ad)
+    print(f"\n[qr] delta={d!r} lapack={ref!r} last pivot column {last}")
+    assert abs(d - ref) <= 1e-9 * abs(ref), (d, ref)
+
+
+@pytest.mark.parametrize("case", ["c1_n64", "c1_n128", "c1_gk31_n128", "c1_em_n64", "c1_pos_n64"])
+def test_qr_newton_iterates_match_reference(case, golden, native_lib):
+    """iteration_method != "TraceSecant": EigenSolver::newtonQRSecantIteration
+    (include/solver.h:210-383) against the iterate list of the compiled reference."""
+    rec = golden["newton_qr"][case]
+    inp = Input(text=cases.input_path(case).read_text().replace('"TraceSecant"', '"QRSecant"'))
+    w, iters, s = solve_once_eigen(inp, inp.initial_guess())
+    print(f"\n[newton-qr] {case}: {len(iters)} iterates, omega={w!r}, ref={rec['final']}, dense_ms={s.stats()['dense_ms']:.2f}")
+    assert len(iters) == len(rec["iterates"]) == rec["final"][2]
+    worst = 0.0
+    for (wi, di), r in zip(iters, rec["iterates"]):
+        rw = complex(r[0], r[1])
+        worst = max(worst, abs(wi - rw) / abs(rw))
+    print(f"[newton-qr] {case}: worst iterate rel err {worst:.3e}")
+    # The bar is the converged eigenvalue (1e-8 relative).  Intermediate iterates of this method can
+    # wander far from the root (c1_pos_n64: 12 iterates, |delta| ~ 1) and the secant quotient
+    # (A - A_old)/delta amplifies rounding-level differences of the assembled matrices by ~1e3 per
+    # iterate until the iteration contracts again: measured 1e-14, 4e-14, 5e-11, 3e-10, 1e-8,
+    # 6e-8 (max), then back down to 2e-11 at convergence.  So: first iterate tight, every iterate
+    # on the reference's trajectory, converged value to the bar.
+    first = complex(*rec["iterates"][0][:2])
+    assert abs(iters[0][0] - first) <= 1e-10 * abs(first)
+    assert worst <= 1e-6
+    rf = complex(rec["final"][0], rec["final"][1])
+    assert abs(w - rf) <= 1e-8 * abs(rf)
+
+
 def test_step_before_seed_is_an_error(native_lib):
     from emme_b200 import EmmeError, capi
     inp = Input(cases.input_path("c1_n32"))
