@@ -284,7 +284,10 @@ def bench_b200(args, rank, local_rank, world):
         capi.check(lib.emme_set_tables(solver._h, *[t.data_ptr() for t in pin_tab]))
 
     def download():
-        capi.check(lib.emme_copy_matrix(solver._h, 0, pin_A.data_ptr()))
+        # eigen_matrix -> pinned host memory on the handle's copy stream: overlaps the next iterate
+        # (the previous step's copy is waited for first, so one buffer is enough)
+        capi.check(lib.emme_copy_wait(solver._h))
+        capi.check(lib.emme_copy_matrix_async(solver._h, 0, pin_A.data_ptr()))
         host_state[:] = (solver.eigen_value.real, solver.eigen_value.imag,
                          solver.d_eigen_value.real, solver.d_eigen_value.imag)
 
@@ -294,6 +297,7 @@ def bench_b200(args, rank, local_rank, world):
     t0 = time.perf_counter()
     run2 = timed_iterates(solver, inp, omega0, args.steps, tol, reseed_points,
                           e2e={"upload": upload, "download": download})
+    capi.check(lib.emme_copy_wait(solver._h))      # the last matrix has landed in host memory
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     if world > 1:

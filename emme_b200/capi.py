@@ -58,6 +58,8 @@ PROTOTYPES = {
     "emme_get_eigen_value": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "emme_trace_delta": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "emme_newton_qr_step": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "emme_copy_matrix_async": (C.c_int, [_vp, C.c_int, _vp]),
+    "emme_copy_wait": (C.c_int, [_vp]),
     "emme_qr_delta": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "emme_qr_step_begin": (C.c_int, [_vp]),
     "emme_shard_config": (C.c_int, [_vp, C.c_int, C.c_int]),

@@ -41,6 +41,10 @@ struct emme_solver {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // emme_copy_matrix_async: device->host copies overlap the next iterate on their own stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_src = nullptr, ev_copy_done = nullptr;
+    bool copy_pending = false;
     emme_params p{};
     int N = 0, dim = 0;
     double *d_eta = nullptr, *d_g = nullptr, *d_bi = nullptr;
@@ -164,6 +168,9 @@ int emme_destroy(emme_solver* s) {
     if (s->sym_graph) cudaGraphExecDestroy(s->sym_graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_copy_src) cudaEventDestroy(s->ev_copy_src);
+    if (s->ev_copy_done) cudaEventDestroy(s->ev_copy_done);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -254,6 +261,11 @@ static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, in
         const int which = dst == s->phys[0] ? 0 : 1;
         ps.n = s->peer_count;
         for (int r = 0; r < s->peer_count; ++r) ps.p[r] = (double2*)s->peer_phys[which][r];
+    }
+    if (s->copy_pending) {
+        // an asynchronous download may still be reading the buffer this assembly overwrites
+        CU(cudaStreamWaitEvent(s->stream, s->ev_copy_done, 0));
+        s->copy_pending = false;
     }
     CU(cudaEventRecord(s->ev0, s->stream));
     CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, ps, shard_index, shard_count,
@@ -754,6 +766,33 @@ int emme_copy_matrix(emme_solver* s, int which, void* host_out) {
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(host_out, src, s->bytes(), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int emme_copy_matrix_async(emme_solver* s, int which, void* pinned_host_out) {
+    if (!s) return fail(-1, "null handle");
+    if (which < 0 || which > 2) return fail(-2, "emme_copy_matrix_async: which must be 0, 1 or 2");
+    if (!pinned_host_out) return fail(-3, "null output");
+    void* src = emme_matrix_device_ptr(s, which);
+    if (!src) return fail(EMME_E_STATE, "matrix not allocated yet (call emme_seed first)");
+    CU(cudaSetDevice(s->device));
+    if (!s->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->ev_copy_src, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_copy_done, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(s->ev_copy_src, s->stream));            // everything that produced the matrix
+    CU(cudaStreamWaitEvent(s->copy_stream, s->ev_copy_src, 0));
+    CU(cudaMemcpyAsync(pinned_host_out, src, s->bytes(), cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaEventRecord(s->ev_copy_done, s->copy_stream));
+    s->copy_pending = true;
+    return 0;
+}
+
+int emme_copy_wait(emme_solver* s) {
+    if (!s) return fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
     return 0;
 }
 

@@ -181,3 +181,12 @@ class ShardedEigenSolver(EigenSolver):
         v = [C.c_double() for _ in range(4)]
         capi.check(self._lib.emme_step_finish(self._h, *[C.byref(x) for x in v]))
         self._pull()
+
+    def newtonQRSecantIteration(self):
+        rc = self._lib.emme_qr_step_begin(self._h)
+        self._pull()
+        capi.check(rc)
+        self._complete()
+        v = [C.c_double() for _ in range(4)]
+        capi.check(self._lib.emme_step_finish(self._h, *[C.byref(x) for x in v]))
+        self._pull()

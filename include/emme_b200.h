@@ -156,6 +156,12 @@ int emme_null_space(emme_solver* s, void* host_out);
 /* which: 0 = eigen_matrix, 1 = eigen_matrix_old, 2 = eigen_matrix_derivative
  * (the three public matrices of EigenSolver, include/solver.h:392-394). */
 int emme_copy_matrix(emme_solver* s, int which, void* host_out);
+/* Asynchronous variant of emme_copy_matrix for PINNED host memory: the copy is ordered after
+ * the work that produced the matrix and runs on its own stream, so it overlaps the next
+ * iterate (eigen_matrix is not overwritten before the iterate after next; the handle makes the
+ * overwriting assembly wait for the copy).  emme_copy_wait blocks until the data has landed. */
+int emme_copy_matrix_async(emme_solver* s, int which, void* pinned_host_out);
+int emme_copy_wait(emme_solver* s);
 int emme_get_stats(const emme_solver* s, emme_stats* out);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing. */
 void* emme_stream(emme_solver* s);

@@ -356,3 +356,22 @@ def test_scan_parallel_single_rank_matches_reference_scan(native_lib):
         assert abs(r["eigenvalue"][0] - ra) < 2e-6 and abs(r["eigenvalue"][1] - rb) < 2e-6, (r, ra, rb)
     bad = parallel.solve_scan_parallel(base.replace('"tokamak"', '"torus"'), "omega_d_coeff", [1.0], -0.8 + 0.25j)
     assert bad[0]["eigenvalue"] == "NaN" and "not supported" in bad[0]["reason"]
+
+
+def test_async_matrix_download_overlaps_and_matches(native_lib):
+    """emme_copy_matrix_async: the download of eigen_matrix into pinned memory is ordered after the
+    iterate that produced it and may overlap the next iterate; the bytes equal the blocking copy."""
+    import torch
+    from emme_b200 import capi
+    inp = Input(cases.input_path("c1_n128"))
+    s = EigenSolver.from_input(inp)
+    s.seed(inp.initial_guess())
+    s.newtonTraceSecantIteration()
+    want = s.eigen_matrix.copy()
+    pin = torch.empty((s.dim, s.dim, 2), dtype=torch.float64).pin_memory()
+    capi.check(s._lib.emme_copy_matrix_async(s._h, 0, pin.data_ptr()))
+    s.newtonTraceSecantIteration()          # overlaps the copy; must not disturb it
+    s.newtonTraceSecantIteration()          # overwrites the copied buffer: waits for the copy
+    capi.check(s._lib.emme_copy_wait(s._h))
+    got = pin.numpy().view(np.complex128).reshape(s.dim, s.dim)
+    assert np.array_equal(got, want)
