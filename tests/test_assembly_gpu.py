@@ -173,3 +173,48 @@ def test_bad_quadrature_order_is_rejected(native_lib):
     with pytest.raises(EmmeError, match="integration_start_points should be 15 or 31") as ei:
         EigenSolver.from_input(inp)
     assert ei.value.code == capi.E_BAD_ORDER
+
+
+def test_bench_workload_full_size(native_lib, monkeypatch):
+    """BASELINE configs[3] at its largest point -- the bench workload, C1 physics with npoints=8192:
+    three rows of A(omega) against the oracle (near, middle and far end of the mesh), the
+    size-independent properties (exact symmetry, diagonal 1 + 1/tau, every entry written), and one
+    Newton/secant iterate through BOTH paths of kernel 2 (symmetric L D L^T and LU) giving the
+    same omega."""
+    import oracle_lib as O
+    inp = Input(cases.input_path("c1"))
+    inp.set_number("npoints", 8192)
+    p, n = inp.params()
+    assert n == 8192
+    eta, g, bi = inp.tables()
+    w = -0.8 + 0.25j
+    s = EigenSolver.from_input(inp)
+    A = s.matrixAssembler(w)
+    st = s.stats()
+    assert st["integrals"] == n * (n - 1) // 2
+    assert np.array_equal(A, A.T)
+    assert np.all(np.diag(A) == 1.0 + 1.0 / p.tau)
+    assert np.isfinite(A.view(np.float64)).all() and np.count_nonzero(A) == A.size
+    scale = float(np.abs(A - np.diag(np.diag(A))).max())
+    for r0 in (0, 4000, 8100):
+        ref, _ = O.assemble(cases.oracle_params(p), eta, g, bi, p.dx, w, rows=(r0, r0 + 1))
+        got, want = A[r0, r0 + 1:], ref[r0, r0 + 1:]
+        d, mag = np.abs(got - want), np.abs(want)
+        print(f"\n[parity] n=8192 row {r0}: max_rel={np.max(d / mag):.3e} strict_frac={(d <= 1e-10 * mag).mean():.6f}")
+        assert (d <= 1e-10 * mag + parity.EPS * scale).all()
+        assert (d <= 1e-10 * mag).mean() >= 0.99
+        del ref
+    del A
+    s.seed(w)
+    s.newtonTraceSecantIteration()
+    assert s.stats()["sym_steps"] == 1 and s.stats()["pivot_fallbacks"] == 0
+    w_sym = s.eigen_value
+    s.close()
+    monkeypatch.setenv("EMME_DENSE_SYM", "0")
+    s2 = EigenSolver.from_input(inp)
+    s2.seed(w)
+    s2.newtonTraceSecantIteration()
+    assert s2.stats()["sym_steps"] == 0 and s2.stats()["pivot_fallbacks"] == 0
+    print(f"[newton] n=8192 first iterate: symmetric path {w_sym!r}, LU path {s2.eigen_value!r}")
+    assert abs(w_sym - s2.eigen_value) <= 1e-11 * abs(w_sym)
+    s2.close()
