@@ -96,6 +96,23 @@ __device__ __forceinline__ void scatter(const RunConst& rc, const PeerSet& A, in
     }
 }
 
+// Per-lane state that is only touched at item or panel boundaries lives in shared memory instead
+// of registers ([field][thread]: conflict-free): the pair constants of the integrand (7 doubles,
+// one load each per evaluation), the current interval and the running sum.  This is what lets five
+// CTAs (20 warps) stay resident per SM without spills (r1j).
+enum { PS_DV, PS_BETA1, PS_CL, PS_S, PS_TWO_OVER_S, PS_HB, PS_C1, PS_FIELDS };
+struct PairSmem {
+    const volatile double* p;     // &s_pair[0][threadIdx.x]
+    __device__ __forceinline__ double f_Dv() const { return p[PS_DV * BLOCK]; }
+    __device__ __forceinline__ double f_beta1() const { return p[PS_BETA1 * BLOCK]; }
+    __device__ __forceinline__ double f_cl() const { return p[PS_CL * BLOCK]; }
+    __device__ __forceinline__ double f_s() const { return p[PS_S * BLOCK]; }
+    __device__ __forceinline__ double f_two_over_s() const { return p[PS_TWO_OVER_S * BLOCK]; }
+    __device__ __forceinline__ double f_hb() const { return p[PS_HB * BLOCK]; }
+    __device__ __forceinline__ double f_c1() const { return p[PS_C1 * BLOCK]; }
+};
+enum { LS_L, LS_R, LS_ABS_TOL, LS_SUM_RE, LS_SUM_IM, LS_FIELDS };
+
 template <int ORDER>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double* __restrict__ gt,
@@ -109,6 +126,10 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
 
     __shared__ double2 s_stack[STACK_SMEM][BLOCK];   // [slot][thread]: conflict-free
     __shared__ int s_pid[STACK_SMEM][BLOCK];         // heap index of the stacked panel (-1: untabulated)
+    __shared__ double s_pair[PS_FIELDS][BLOCK];
+    __shared__ double s_lane[LS_FIELDS][BLOCK];
+    volatile double* const lane_state = &s_lane[0][threadIdx.x];
+    const PairSmem pc{&s_pair[0][threadIdx.x]};
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -119,11 +140,8 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
     bool active = false;
     bool warp_exhausted = false;
     int it_i = 0, it_j = 0, it_m = 0, top = 0, pid = 0;
-    PairConst pc;
-    cplx sum = mk(0., 0.);
-    double abs_tol = 0., l = 0., r = 0.;
     EvalCounters cnt{0u, 0u};
-    unsigned long long n_eval = 0, n_panel = 0, n_int = 0;
+    unsigned int n_eval32 = 0, n_panel32 = 0, n_int32 = 0;   // per thread: far below 2^32
     int max_top = 0;
 
     for (;;) {
@@ -144,11 +162,22 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                     const unsigned long long kg = (k >> 5) * (shard_count << 5) + (shard_index << 5) + (k & 31);
                     it_m = (int)(kg / n_pairs);
                     decode_pair(kg - (unsigned long long)it_m * n_pairs, rc.N, it_i, it_j);
-                    pc = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
-                    sum = mk(0., 0.);
-                    abs_tol = 0.;
-                    l = 0.0;
-                    r = rc.half_pi;
+                    {
+                        const PairConst c = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
+                        volatile double* ps = &s_pair[0][threadIdx.x];
+                        ps[PS_DV * BLOCK] = c.Dv;
+                        ps[PS_BETA1 * BLOCK] = c.beta1;
+                        ps[PS_CL * BLOCK] = c.cl;
+                        ps[PS_S * BLOCK] = c.s;
+                        ps[PS_TWO_OVER_S * BLOCK] = c.two_over_s;
+                        ps[PS_HB * BLOCK] = c.hb;
+                        ps[PS_C1 * BLOCK] = c.c1;
+                    }
+                    lane_state[LS_SUM_RE * BLOCK] = 0.;
+                    lane_state[LS_SUM_IM * BLOCK] = 0.;
+                    lane_state[LS_ABS_TOL * BLOCK] = 0.;
+                    lane_state[LS_L * BLOCK] = 0.0;
+                    lane_state[LS_R * BLOCK] = rc.half_pi;
                     top = 0;
                     pid = 0;
                     active = true;
@@ -161,8 +190,6 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
             continue;
         }
         // ---- one Gauss-Kronrod panel per active lane, nodes in lockstep ----
-        const double mid = (r + l) / 2;
-        const double scale = (r - l) / 2;
         cplx K = mk(0., 0.), G = mk(0., 0.), fplus = mk(0., 0.);
 #pragma unroll 1
         for (int j = 0; j <= 2 * H; ++j) {
@@ -181,10 +208,12 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                     nt.x = e1.y;
                 } else {
                     // node position exactly as the reference forms it: scale*x + mid, no FMA
+                    const double l = lane_state[LS_L * BLOCK], r = lane_state[LS_R * BLOCK];
+                    const double mid = (r + l) / 2, scale = (r - l) / 2;
                     nt = node_trig(__dadd_rn(__dmul_rn(scale, node), mid));
                 }
                 const cplx fx = eval_node(rc, pc, it_m, nt, cnt);
-                ++n_eval;
+                ++n_eval32;
                 if (j == 0) {
                     K = mk(T.kw[0] * fx.re, T.kw[0] * fx.im);
                     G = mk(T.gw[0] * fx.re, T.gw[0] * fx.im);
@@ -203,14 +232,20 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
             }
         }
         if (active) {
-            ++n_panel;
+            ++n_panel32;
             // ---- accept / bisect (include/functions.h:233-247) ----
+            const double l = lane_state[LS_L * BLOCK], r = lane_state[LS_R * BLOCK];
+            const double mid = (r + l) / 2, scale = (r - l) / 2;
+            double abs_tol = lane_state[LS_ABS_TOL * BLOCK];
             const cplx integral = mk(K.re * scale, K.im * scale);
             const double e0 = fmax(hypot(K.re - G.re, K.im - G.im),
                                    hypot(K.re, K.im) * 2.220446049250313e-16 * 2);
             const double err = e0 * scale;
             const double rel = hypot(rc.tol * integral.re, rc.tol * integral.im);
-            if (abs_tol == 0.) abs_tol = rel;
+            if (abs_tol == 0.) {
+                abs_tol = rel;
+                lane_state[LS_ABS_TOL * BLOCK] = rel;
+            }
             const bool split = ldexp(scale, rc.maxdepth) > rc.thr_len &&
                                err > abs_tol * rc.inv_scale + rc.prec && err > rel + rc.prec;
             if (split) {
@@ -226,22 +261,25 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                 }
                 ++top;
                 max_top = max(max_top, top);
-                r = mid;
+                lane_state[LS_R * BLOCK] = mid;
                 pid = right >= 0 ? right - 1 : -1;
             } else {
-                sum = sum + integral;
+                const cplx sum = mk(lane_state[LS_SUM_RE * BLOCK] + integral.re,
+                                    lane_state[LS_SUM_IM * BLOCK] + integral.im);
                 if (top > 0) {
+                    lane_state[LS_SUM_RE * BLOCK] = sum.re;
+                    lane_state[LS_SUM_IM * BLOCK] = sum.im;
                     --top;
                     const double2 e = top < STACK_SMEM ? s_stack[top][threadIdx.x] : my_spill[top - STACK_SMEM];
                     pid = top < STACK_SMEM ? s_pid[top][threadIdx.x] : -1;
-                    l = e.x;
-                    r = e.y;
+                    lane_state[LS_L * BLOCK] = e.x;
+                    lane_state[LS_R * BLOCK] = e.y;
                 } else {
                     // ---- finalize: kappa = -i*pref*sum (+ electron part), scatter ----
                     cplx kap = mk(rc.kappa_pref * sum.im, -rc.kappa_pref * sum.re);
-                    if (it_m > 0) kap = kap + kappa_e(rc, it_m, pc.deta, gt[it_i] - gt[it_j]);
+                    if (it_m > 0) kap = kap + kappa_e(rc, it_m, eta[it_i] - eta[it_j], gt[it_i] - gt[it_j]);
                     scatter(rc, A, it_i, it_j, it_m, kap);
-                    ++n_int;
+                    ++n_int32;
                     active = false;
                 }
             }
@@ -249,6 +287,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
     }
     // ---- counters ----
     unsigned long long n_fwd = cnt.fwd, n_bwd = cnt.bwd;
+    unsigned long long n_eval = n_eval32, n_panel = n_panel32, n_int = n_int32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);

@@ -40,15 +40,37 @@ EMME_HD cplx operator*(cplx a, cplx b) {
 EMME_HD cplx operator*(double s, cplx a) { return mk(s * a.re, s * a.im); }
 EMME_HD cplx conj(cplx a) { return mk(a.re, -a.im); }
 EMME_HD double norm2(cplx a) { return a.re * a.re + a.im * a.im; }
+// 1/x and 1/sqrt(x) for positive, normal x: hardware seed (MUFU, >= 20 bits) + two Newton steps in
+// FMAs -- within 1 ulp, 9 issue slots instead of the ~25 of the correctly rounded library division
+// (whose special-case handling this kernel never needs: x is |lambda|^2, |mu|^2 or 1 + u^2).  The
+// kernel is issue-slot bound, so these count.
+EMME_HD double rcp_pos(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;         // host build (tests/emul) only
+#endif
+}
 EMME_HD cplx recip(cplx a) {
-    const double d = 1.0 / norm2(a);
+    const double d = rcp_pos(norm2(a));
     return mk(a.re * d, -a.im * d);
 }
 // i*a
 EMME_HD cplx mul_i(cplx a) { return mk(-a.im, a.re); }
 EMME_HD double rsqrt_(double x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);     // (1 - x y^2)/2
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
 #else
     return 1.0 / sqrt(x);   // host build (tests/emul) only
 #endif
@@ -99,6 +121,15 @@ struct PairConst {
     double hb;      // 0.5*(b+b')
     double bsum;    // b+b'
     double c1;      // -omega_s_i*eta_i*s
+    // accessors: eval_node is generic over where the pair constants live (this struct on the host
+    // emulation, shared memory in the kernel -- see PairSmem in assembly.cu)
+    EMME_HD double f_Dv() const { return Dv; }
+    EMME_HD double f_beta1() const { return beta1; }
+    EMME_HD double f_cl() const { return cl; }
+    EMME_HD double f_s() const { return s; }
+    EMME_HD double f_two_over_s() const { return two_over_s; }
+    EMME_HD double f_hb() const { return hb; }
+    EMME_HD double f_c1() const { return c1; }
 };
 
 EMME_HD PairConst make_pair(const RunConst& rc, double eta, double etap, double g, double gp,
@@ -142,9 +173,22 @@ EMME_HD bool le_nonneg(double a, double b) {
 
 EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalCounters& cnt) {
     const double THRESHOLD = 2.e+7;
-    const double az = sqrt(norm2(z));
+    // n0 = floor(|z|) + 1 (include/functions.h:384) without a double-precision square root: FP32
+    // estimate, then the exact integer fix-up against |z|^2 (n*n is exact in FP64).  floor of the
+    // exact root and floor of the rounded root differ only if |z| lies within an ulp of an integer.
+    const double n2 = norm2(z);
+#if defined(__CUDA_ARCH__)
+    int n0 = (int)__fsqrt_rn((float)n2);
+#else
+    int n0 = (int)sqrtf((float)n2);
+#endif
+    {
+        const double d0 = (double)n0;
+        if (d0 * d0 > n2) --n0;
+        else if (fma(d0, d0, 2.0 * d0 + 1.0) <= n2) ++n0;
+    }
+    n0 += 1;
     // the order n is carried as an int (loop control, integer pipe) and as a double (exact)
-    const int n0 = (int)(floor(az) + 1.0);
     int n = n0;
     double dn = (double)n0;
     // Forward recurrence p_{k+1} = p_{k-1} - (2n/z) p_k until |p|^2 exceeds the threshold.  Only the
@@ -153,7 +197,7 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     // otherwise idle FP32 pipe (relative error ~1e-6 in |p|^2 can move N by one only when |p_N|^2
     // sits within 1e-6 of the threshold).  Two trips per round, no register moves.  (A speculative
     // four-trips-per-round variant that takes the tests off the critical path measured no faster.)
-    if (az >= 1e-5) {
+    if (n2 >= 1e-10) {
         const float thr2 = (float)(THRESHOLD * THRESHOLD);
         const float zr = (float)zc.re, zi = (float)zc.im;
         float fn = (float)n0;
@@ -181,7 +225,7 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
         // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared:
         // max(T*n*|2/z|, T^2).  The first term only wins for |z| < n*1e-7 (FP64 here: rare, and the
         // products overflow FP32).
-        const double thr2 = fmax(THRESHOLD * (dn * (2.0 / az)), THRESHOLD * THRESHOLD);
+        const double thr2 = fmax(THRESHOLD * (dn * (2.0 / sqrt(n2))), THRESHOLD * THRESHOLD);
         cplx pa = mk(0., 0.), pb = mk(1., 0.);   // pa = p_{k-1}, pb = p_k
         for (;;) {
             if (!le_nonneg(norm2(pb), thr2)) break;
@@ -325,7 +369,8 @@ EMME_HD cplx cexp_lean(double a, double b) {
 }
 
 // g(x) for mode m (0, 1, 2) at the node described by nt.
-EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, const NodeTrig& nt,
+template <class PC>
+EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeTrig& nt,
                        EvalCounters& cnt) {
     const double t = nt.t, it = nt.it;
     // contour rotation e = exp(-i*omi*atan(u)), u = t/arc, tau~ = t*e (src/Parameters.cpp:121-124):
@@ -339,30 +384,33 @@ EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, const Nod
     const double jd = rc.omi * u * (rs * rs);
     const cplx jacob = e - jd * mul_i(e);
     // lambda = 1 + i*cl*tau~ (:101-106, :131)
-    const cplx lambda = mk(1.0 - pc.cl * taut.im, pc.cl * taut.re);
+    const double cl = pc.f_cl();
+    const cplx lambda = mk(1.0 - cl * taut.im, cl * taut.re);
     const cplx il = recip(lambda);
-    const cplx z = pc.s * il;                  // sqrt(b b')/lambda  (:135-136)
-    const cplx zc = pc.two_over_s * lambda;    // 2/z
+    const cplx z = pc.f_s() * il;                  // sqrt(b b')/lambda  (:135-136)
+    const cplx zc = pc.f_two_over_s() * lambda;    // 2/z
     const cplx z4 = z.re < 0 ? z : -z;         // include/functions.h:407
     // nu = qR*deta/(vt*tau~) = (D/vt)/t * conj(e)   (:140)
     const cplx itaut = it * conj(e);           // 1/tau~
-    const cplx nu = pc.Dv * itaut;
+    const cplx nu = pc.f_Dv() * itaut;
     const cplx nu2 = nu * nu;
     // log of the exponential factor (:157-164); 2 + i*beta1/nu == 2*lambda
-    const cplx L = (-0.5) * nu2 + (0.5 * pc.beta1) * mk(nu.im, -nu.re) +
-                   mul_i(taut * mk(rc.wr, rc.wi)) - pc.hb * il;
+    const double hb = pc.f_hb();
+    const cplx L = (-0.5) * nu2 + (0.5 * pc.f_beta1()) * mk(nu.im, -nu.re) +
+                   mul_i(taut * mk(rc.wr, rc.wi)) - hb * il;
     const cplx arg = L - z4;
     if (arg.re < -40.) return mk(0., 0.);      // safe_exp underflow guard (:167-173)
 
     cplx y0, y1, mu;
     bessel_i_alter(z, zc, y0, y1, mu, cnt);
 
-    const cplx il3 = il * il * il;             // pow(lambda, -3.)   (:138-139)
-    // i0_coef, i1_coef (:142-151)
+    // i0_coef*y0 + i1_coef*y1 (:142-151) with pow(lambda, -3.) = il^3 factored as il * il^2:
+    //   i0 = il*(A + B*il^2),  i1 = il*(c1*il^2),  A = omega - omega_s_i*inner,  B = wsi_etai*(hb - lambda)
+    const cplx il2 = il * il;
     const cplx inner = mk(1.0 + rc.eta_i * (0.5 * nu2.re - 1.5), rc.eta_i * (0.5 * nu2.im));
-    const cplx i0 = (mk(rc.wr, rc.wi) - rc.omega_s_i * inner) * il +
-                    rc.wsi_etai * (mk(pc.hb, 0.) - lambda) * il3;
-    const cplx i1 = pc.c1 * il3;
+    const cplx A = mk(rc.wr, rc.wi) - rc.omega_s_i * inner;
+    const cplx B = rc.wsi_etai * (mk(hb, 0.) - lambda);
+    const cplx S = (A + B * il2) * y0 + (pc.f_c1() * il2) * y1;
 
 #if EMME_LEAN_CEXP
     const cplx se = cexp_lean(arg.re, arg.im);
@@ -373,8 +421,10 @@ EMME_HD cplx eval_node(const RunConst& rc, const PairConst& pc, int m, const Nod
     cplx pw = itaut;                           // nu^m / tau~        (:174)
     if (m >= 1) pw = pw * nu;
     if (m >= 2) pw = pw * nu;
-    const cplx f = pw * jacob * se * (i0 * y0 + i1 * y1) * recip(mu);
-    return nt.icsq * f;                        // f(tan x)/cos^2 x, include/functions.h:317
+    // f = pw * jacob * se * il * S / mu, 1/mu = conj(mu)/|mu|^2 with the real factor applied last
+    const cplx f = (pw * jacob * se) * ((il * S) * conj(mu));
+    const double sc = nt.icsq * rcp_pos(norm2(mu));
+    return sc * f;                             // f(tan x)/cos^2 x, include/functions.h:317
 }
 
 // Closed-form electron part (src/Parameters.cpp:186-209), m = 1, 2 (m = 0 is zero).
