@@ -40,7 +40,7 @@ constexpr int BLOCK = 128;
 constexpr int TRIG_DEPTH = 8;                           // node table covers bisection levels 0..8
 constexpr int TRIG_PANELS = (1 << (TRIG_DEPTH + 1)) - 1;   // heap-ordered panels
 #ifndef EMME_ASM_MIN_BLOCKS
-#define EMME_ASM_MIN_BLOCKS 4
+#define EMME_ASM_MIN_BLOCKS 5
 #endif
 constexpr int MIN_BLOCKS = EMME_ASM_MIN_BLOCKS;
 
@@ -120,7 +120,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                 unsigned long long n_items_local, unsigned long long shard_index,
                 unsigned long long shard_count, unsigned long long* __restrict__ counter,
                 double2* __restrict__ spill, int spill_cap, unsigned long long* __restrict__ stats,
-                int refill_min, const double4* __restrict__ trig) {
+                int refill_min, const NodeConst* __restrict__ table) {
     constexpr int H = (ORDER - 1) / 2;          // 7 or 15 symmetric node pairs
     const GKTables& T = ORDER == 15 ? c_gk15 : c_gk31;
 
@@ -196,23 +196,26 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
             const int ni = (j + 1) >> 1;                       // node index 0..H
             const double node = (j & 1) ? T.a[ni] : -T.a[ni];  // j = 0: -0*scale + mid = mid
             if (active) {
-                NodeTrig nt;
+                NodeConst nc;
                 if (pid >= 0) {
-                    // tabulated panel: tan x, 1/tan x, 1/cos^2 x of this node (built by trig_table_kernel
-                    // with the very same node_trig() and node position arithmetic)
-                    const double2* e = reinterpret_cast<const double2*>(trig + (size_t)pid * (2 * H + 1) + j);
-                    const double2 e0 = __ldg(e), e1 = __ldg(e + 1);
-                    nt.t = e0.x;
-                    nt.it = e0.y;
-                    nt.icsq = e1.x;
-                    nt.x = e1.y;
+                    // tabulated panel: the node constants of this (panel, node) for this omega, built
+                    // by node_table_kernel with the very same node_const() and node position arithmetic
+                    const double2* e = reinterpret_cast<const double2*>(table + (size_t)pid * (2 * H + 1) + j);
+                    const double2 e0 = __ldg(e), e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3),
+                                  e4 = __ldg(e + 4), e5 = __ldg(e + 5);
+                    nc.taut = mk(e0.x, e0.y);
+                    nc.itaut = mk(e1.x, e1.y);
+                    nc.it2 = mk(e2.x, e2.y);
+                    nc.M = mk(e3.x, e3.y);
+                    nc.pj = mk(e4.x, e4.y);
+                    nc.icsq = e5.x;
                 } else {
                     // node position exactly as the reference forms it: scale*x + mid, no FMA
                     const double l = lane_state[LS_L * BLOCK], r = lane_state[LS_R * BLOCK];
                     const double mid = (r + l) / 2, scale = (r - l) / 2;
-                    nt = node_trig(__dadd_rn(__dmul_rn(scale, node), mid));
+                    nc = node_const(rc, __dadd_rn(__dmul_rn(scale, node), mid));
                 }
-                const cplx fx = eval_node(rc, pc, it_m, nt, cnt);
+                const cplx fx = eval_node(rc, pc, it_m, nc, cnt);
                 ++n_eval32;
                 if (j == 0) {
                     K = mk(T.kw[0] * fx.re, T.kw[0] * fx.im);
@@ -309,9 +312,10 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
 
 // Node table: one thread per (panel, node) walks from the root panel [0, pi/2] down to its panel
 // with the bisection arithmetic of gauss_kronrod_adaptive (mid = (r+l)/2), forms the node
-// position like the quadrature does and stores node_trig() of it.
+// position like the quadrature does and stores node_const() of it.  The constants depend on omega
+// and arc_coeff, so the table is rebuilt at the start of every assembly (7,665 / 15,841 entries).
 template <int ORDER>
-__global__ void trig_table_kernel(double4* __restrict__ trig, double half_pi) {
+__global__ void node_table_kernel(NodeConst* __restrict__ table, const RunConst rc) {
     constexpr int H = (ORDER - 1) / 2;
     const GKTables& T = ORDER == 15 ? c_gk15 : c_gk31;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,7 +324,7 @@ __global__ void trig_table_kernel(double4* __restrict__ trig, double half_pi) {
     int depth = 0;
     while ((1 << (depth + 1)) - 1 <= p) ++depth;
     const int idx = p - ((1 << depth) - 1);
-    double l = 0.0, r = half_pi;
+    double l = 0.0, r = rc.half_pi;
     for (int b = depth - 1; b >= 0; --b) {
         const double mid = (r + l) / 2;
         if ((idx >> b) & 1) l = mid; else r = mid;
@@ -328,18 +332,17 @@ __global__ void trig_table_kernel(double4* __restrict__ trig, double half_pi) {
     const double mid = (r + l) / 2, scale = (r - l) / 2;
     const int ni = (j + 1) >> 1;
     const double node = (j & 1) ? T.a[ni] : -T.a[ni];
-    const NodeTrig nt = node_trig(__dadd_rn(__dmul_rn(scale, node), mid));
-    trig[e] = make_double4(nt.t, nt.it, nt.icsq, nt.x);
+    table[e] = node_const(rc, __dadd_rn(__dmul_rn(scale, node), mid));
 }
 
-size_t assembly_trig_table_bytes(int order) { return sizeof(double4) * (size_t)TRIG_PANELS * order; }
+size_t assembly_node_table_bytes(int order) { return sizeof(NodeConst) * (size_t)TRIG_PANELS * order; }
 
-cudaError_t build_trig_table(int order, void* trig, double half_pi, cudaStream_t stream) {
-    const int n = TRIG_PANELS * order;
-    if (order == 15)
-        trig_table_kernel<15><<<(n + 127) / 128, 128, 0, stream>>>((double4*)trig, half_pi);
+static cudaError_t build_node_table(const RunConst& rc, void* table, cudaStream_t stream) {
+    const int n = TRIG_PANELS * rc.order;
+    if (rc.order == 15)
+        node_table_kernel<15><<<(n + 127) / 128, 128, 0, stream>>>((NodeConst*)table, rc);
     else
-        trig_table_kernel<31><<<(n + 127) / 128, 128, 0, stream>>>((double4*)trig, half_pi);
+        node_table_kernel<31><<<(n + 127) / 128, 128, 0, stream>>>((NodeConst*)table, rc);
     return cudaGetLastError();
 }
 
@@ -381,7 +384,7 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
                             const double* bi, const PeerSet& A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches, int refill_min, const void* trig) {
+                            unsigned long long* n_launches, int refill_min, void* table) {
     const unsigned long long N = rc.N;
     const unsigned long long n_items = N * (N - 1) / 2 * (rc.em ? 3ULL : 1ULL);
     const unsigned long long sc = shard_count, si = shard_index;
@@ -398,6 +401,9 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
+    e = build_node_table(rc, table, stream);
+    if (e != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
     if (shard_index == 0) {
         diagonal_kernel<<<(rc.N + 127) / 128, 128, 0, stream>>>(rc, bi, A);
         if (n_launches) ++*n_launches;
@@ -407,11 +413,11 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
         if (rc.order == 15) {
             assemble_kernel<15><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats, refill_min, (const double4*)trig);
+                stats, refill_min, (const NodeConst*)table);
         } else {
             assemble_kernel<31><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats, refill_min, (const double4*)trig);
+                stats, refill_min, (const NodeConst*)table);
         }
     }
     return cudaGetLastError();

@@ -26,9 +26,9 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
                             const double* bi, const PeerSet& A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches, int refill_min, const void* trig);
+                            unsigned long long* n_launches, int refill_min, void* node_table);
 
-// per-order table of node_trig() for the first bisection levels (built once per handle)
-size_t assembly_trig_table_bytes(int order);
-cudaError_t build_trig_table(int order, void* trig, double half_pi, cudaStream_t stream);
+// scratch for the table of node_const() of the first bisection levels; launch_assembly rebuilds
+// it at the start of every assembly (its entries depend on omega and arc_coeff)
+size_t assembly_node_table_bytes(int order);
 }  // namespace emme

@@ -223,9 +223,7 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
                               emme::assembly_groups_per_block(p->integration_start_points);
         CU(cudaMalloc(&s->d_spill, groups * s->spill_cap * sizeof(double2)));
     }
-    CU(cudaMalloc(&s->d_trig, emme::assembly_trig_table_bytes(p->integration_start_points)));
-    CU(emme::build_trig_table(p->integration_start_points, s->d_trig, M_PI / 2.0, s->stream));
-    ++s->launches;
+    CU(cudaMalloc(&s->d_trig, emme::assembly_node_table_bytes(p->integration_start_points)));
     CU(cudaMalloc(&s->d_trace, sizeof(double2)));
     CU(cudaMalloc(&s->d_info, sizeof(int)));
     CU(cudaMalloc(&s->d_flag, sizeof(int)));

@@ -291,6 +291,42 @@ EMME_HD NodeTrig node_trig(double x) {
     return n;
 }
 
+// Everything the integrand needs of a quadrature node that does NOT depend on the pair (eta, eta'):
+// the contour rotation e = exp(-i*omi*atan(u)), u = t/arc (src/Parameters.cpp:121-124), and what is
+// built from it and from omega.  One definition for the per-assembly node table
+// (assembly.cu::node_table_kernel), the direct path below the table and the host emulation.
+struct NodeConst {
+    cplx taut;    // tau~ = t*e
+    cplx itaut;   // 1/tau~ = conj(e)/t
+    cplx it2;     // (1/tau~)^2
+    cplx M;       // i*tau~*omega                       (:160)
+    cplx pj;      // jacobian/tau~                      (:126-129, :174)
+    double icsq;  // 1/cos^2 x                          (include/functions.h:317)
+    double pad;
+};
+
+EMME_HD NodeConst node_const(const RunConst& rc, double x) {
+    const NodeTrig nt = node_trig(x);
+    const double t = nt.t, it = nt.it;
+    // cos(atan u) = 1/sqrt(1+u^2), sin(atan u) = u/sqrt(1+u^2) -- no atan, no second sincos
+    const double u = t * rc.inv_arc;
+    const double w1 = 1.0 + u * u;
+    const double rs = rsqrt_(w1);
+    const cplx e = mk(rs, -rc.omi * (u * rs));
+    // jacobian: e - i*e*omi*t/(arc*(1+u^2)) = e - i*e*omi*u/(1+u^2), 1/(1+u^2) = rs^2
+    const double jd = rc.omi * u * (rs * rs);
+    const cplx jacob = e - jd * mul_i(e);
+    NodeConst nc;
+    nc.taut = t * e;
+    nc.itaut = it * conj(e);
+    nc.it2 = nc.itaut * nc.itaut;
+    nc.M = mul_i(nc.taut * mk(rc.wr, rc.wi));
+    nc.pj = nc.itaut * jacob;
+    nc.icsq = nt.icsq;
+    nc.pad = 0.;
+    return nc;
+}
+
 // exp(a + i b) for the integrand's exponential factor: a is known to lie in [-40, ~60] (the
 // underflow guard has already removed a < -40), so the general-purpose exp()/sincos() of the CUDA
 // math library -- 48 + 74 instructions per call, two thirds of them range/special-case handling on
@@ -368,36 +404,24 @@ EMME_HD cplx cexp_lean(double a, double b) {
     return cexp_lib(a, b);
 }
 
-// g(x) for mode m (0, 1, 2) at the node described by nt.
+// g(x) for mode m (0, 1, 2) at the node described by nc.
 template <class PC>
-EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeTrig& nt,
+EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeConst& nc,
                        EvalCounters& cnt) {
-    const double t = nt.t, it = nt.it;
-    // contour rotation e = exp(-i*omi*atan(u)), u = t/arc, tau~ = t*e (src/Parameters.cpp:121-124):
-    // cos(atan u) = 1/sqrt(1+u^2), sin(atan u) = u/sqrt(1+u^2) -- no atan, no second sincos
-    const double u = t * rc.inv_arc;
-    const double w1 = 1.0 + u * u;
-    const double rs = rsqrt_(w1);
-    const cplx e = mk(rs, -rc.omi * (u * rs));
-    const cplx taut = t * e;
-    // jacobian (:126-129): e - i*e*omi*t/(arc*(1+u^2)) = e - i*e*omi*u/(1+u^2), 1/(1+u^2) = rs^2
-    const double jd = rc.omi * u * (rs * rs);
-    const cplx jacob = e - jd * mul_i(e);
     // lambda = 1 + i*cl*tau~ (:101-106, :131)
     const double cl = pc.f_cl();
-    const cplx lambda = mk(1.0 - cl * taut.im, cl * taut.re);
+    const cplx lambda = mk(1.0 - cl * nc.taut.im, cl * nc.taut.re);
     const cplx il = recip(lambda);
     const cplx z = pc.f_s() * il;                  // sqrt(b b')/lambda  (:135-136)
     const cplx zc = pc.f_two_over_s() * lambda;    // 2/z
     const cplx z4 = z.re < 0 ? z : -z;         // include/functions.h:407
-    // nu = qR*deta/(vt*tau~) = (D/vt)/t * conj(e)   (:140)
-    const cplx itaut = it * conj(e);           // 1/tau~
-    const cplx nu = pc.f_Dv() * itaut;
-    const cplx nu2 = nu * nu;
+    // nu = qR*deta/(vt*tau~) = (D/vt)/tau~   (:140)
+    const double Dv = pc.f_Dv();
+    const cplx nu = Dv * nc.itaut;
+    const cplx nu2 = (Dv * Dv) * nc.it2;
     // log of the exponential factor (:157-164); 2 + i*beta1/nu == 2*lambda
     const double hb = pc.f_hb();
-    const cplx L = (-0.5) * nu2 + (0.5 * pc.f_beta1()) * mk(nu.im, -nu.re) +
-                   mul_i(taut * mk(rc.wr, rc.wi)) - hb * il;
+    const cplx L = (-0.5) * nu2 + (0.5 * pc.f_beta1()) * mk(nu.im, -nu.re) + nc.M - hb * il;
     const cplx arg = L - z4;
     if (arg.re < -40.) return mk(0., 0.);      // safe_exp underflow guard (:167-173)
 
@@ -418,12 +442,12 @@ EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeTrig& 
     const cplx se = cexp_lib(arg.re, arg.im);
 #endif
 
-    cplx pw = itaut;                           // nu^m / tau~        (:174)
+    cplx pw = nc.pj;                           // nu^m / tau~ * jacobian   (:174)
     if (m >= 1) pw = pw * nu;
     if (m >= 2) pw = pw * nu;
-    // f = pw * jacob * se * il * S / mu, 1/mu = conj(mu)/|mu|^2 with the real factor applied last
-    const cplx f = (pw * jacob * se) * ((il * S) * conj(mu));
-    const double sc = nt.icsq * rcp_pos(norm2(mu));
+    // f = pw * se * il * S / mu, 1/mu = conj(mu)/|mu|^2 with the real factor applied last
+    const cplx f = (pw * se) * ((il * S) * conj(mu));
+    const double sc = nc.icsq * rcp_pos(norm2(mu));
     return sc * f;                             // f(tan x)/cos^2 x, include/functions.h:317
 }
 

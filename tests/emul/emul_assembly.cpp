@@ -84,7 +84,7 @@ extern "C" int emul_assemble(const emme_params* p, int N, const double* eta, con
                 const double node = gl <= H ? T.a[nidx] : -T.a[nidx];
                 volatile double prod = scale * node;  // no FMA, as __dmul_rn/__dadd_rn
                 const double x = prod + mid;
-                fx[gl] = eval_node(rc, pc, it_m, node_trig(x), cnt);
+                fx[gl] = eval_node(rc, pc, it_m, node_const(rc, x), cnt);
                 ++n_eval;
             }
             cplx K = mk(T.kw[0] * fx[0].re, T.kw[0] * fx[0].im);
