@@ -17,6 +17,7 @@
 // only ever calls them from kernels.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define EMME_HD __host__ __device__ __forceinline__
@@ -195,13 +196,16 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     // STOPPING INDEX N is used below (the backward pass restarts from y_N = 1), and the result does
     // not depend on it beyond 1/|p_N|^2 ~ 2.5e-15: the search therefore runs in FP32 on the
     // otherwise idle FP32 pipe (relative error ~1e-6 in |p|^2 can move N by one only when |p_N|^2
-    // sits within 1e-6 of the threshold).  Two trips per round, no register moves.  (A speculative
-    // four-trips-per-round variant that takes the tests off the critical path measured no faster.)
+    // sits within 1e-6 of the threshold).
     if (n2 >= 1e-10) {
         const float thr2 = (float)(THRESHOLD * THRESHOLD);
         const float zr = (float)zc.re, zi = (float)zc.im;
         float fn = (float)n0;
-        float par = 0.f, pai = 0.f, pbr = 1.f, pbi = 0.f;   // pa = p_{k-1}, pb = p_k
+        float par = 0.f, pai = 0.f, pbr = 1.f, pbi = 0.f;   // pa = p_{k-1}, pb = p_k, k = n0 + 2*rounds
+        // Two trips per round with ONE threshold test (the kernel is issue bound: the test is a
+        // third of a trip).  When p_k fails the test the round before may already have produced
+        // p_{k-1} above the threshold: checked once on exit.  |p| <= 2e7 grows by at most
+        // (n |2/z|)^2 <= 1e13 per untested round, far below FLT_MAX.
         for (;;) {
             if (!(fmaf(pbr, pbr, pbi * pbi) <= thr2)) break;
             {
@@ -210,16 +214,15 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
                 pai = fmaf(-cr, pbi, fmaf(-ci, pbr, pai));
             }
             fn += 1.0f;
-            ++n;
-            if (!(fmaf(par, par, pai * pai) <= thr2)) break;
             {
                 const float cr = fn * zr, ci = fn * zi;
                 pbr = fmaf(-cr, par, fmaf(ci, pai, pbr));     // pb <- p_{k+2}
                 pbi = fmaf(-cr, pai, fmaf(-ci, par, pbi));
             }
             fn += 1.0f;
-            ++n;
         }
+        if (!(fmaf(par, par, pai * pai) <= thr2)) fn -= 1.0f;  // p_{k-1} was the first above the threshold
+        n = (int)fn;
         dn = (double)n;
     } else {
         // test_1 = max(sqrt(T*|p1|*|p0 - 2n/z*p1|), T) with p0 = 0, p1 = 1; compared squared:
@@ -251,6 +254,20 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     const double sgB = neg ? -sgA : sgA;
     cplx ya = mk(1., 0.), yb = mk(0., 0.);   // ya = y_k ("y0"), yb = y_{k+1} ("y1")
     mu = mk(0., 0.);
+    for (; n >= 4; n -= 4) {                 // four trips per round: a quarter of the loop control
+        yb = cfma(dn * zc, ya, yb);
+        mu = mk(fma(sgA, ya.re, mu.re), fma(sgA, ya.im, mu.im));
+        dn -= 1.0;
+        ya = cfma(dn * zc, yb, ya);
+        mu = mk(fma(sgB, yb.re, mu.re), fma(sgB, yb.im, mu.im));
+        dn -= 1.0;
+        yb = cfma(dn * zc, ya, yb);
+        mu = mk(fma(sgA, ya.re, mu.re), fma(sgA, ya.im, mu.im));
+        dn -= 1.0;
+        ya = cfma(dn * zc, yb, ya);
+        mu = mk(fma(sgB, yb.re, mu.re), fma(sgB, yb.im, mu.im));
+        dn -= 1.0;
+    }
     for (; n >= 2; n -= 2) {
         yb = cfma(dn * zc, ya, yb);          // yb <- y_{k-1}; ya is now "y1"
         mu = mk(fma(sgA, ya.re, mu.re), fma(sgA, ya.im, mu.im));
@@ -340,11 +357,60 @@ EMME_HD NodeConst node_const(const RunConst& rc, double x) {
 #define EMME_LEAN_CEXP 0
 #endif
 
-EMME_HD double two_to(int k) {          // 2^k for -1022 <= k <= 1023
+// coefficients of cexp_lean: in __constant__ memory on the device so that they are direct
+// c[bank][offset] operands of the DFMAs (as immediates each 64-bit constant costs two UMOVs)
+#define EMME_CEXP_COEFFS                                                                            \
+    {6.36619772367581382433e-01,  /*  0 2/pi                        */                               \
+     1.57079632673412561417e+00,  /*  1 pi/2, first 33 bits         */                               \
+     6.07710050630396597660e-11,  /*  2 pi/2, next 33 bits          */                               \
+     2.02226624879595063154e-21,  /*  3 pi/2, tail                  */                               \
+     1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,            \
+     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, /* 4-9 S6..S1 */ \
+     -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,           \
+     2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02, /* 10-15 C6..C1 */ \
+     1.44269504088896338700e+00,  /* 16 log2(e)                     */                               \
+     6.93147180369123816490e-01,  /* 17 ln2, first 33 bits          */                               \
+     1.90821492927058770002e-10,  /* 18 ln2, tail                   */                               \
+     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,     \
+     2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,     \
+     8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, /* 19-29: 1/13! .. 1/3! */ \
+     6755399441055744.0}          /* 30 1.5*2^52: round-to-nearest-integer trick */
+#if defined(__CUDACC__)
+static __constant__ double c_cexp[31] = EMME_CEXP_COEFFS;
+#endif
+static const double h_cexp[31] = EMME_CEXP_COEFFS;
 #if defined(__CUDA_ARCH__)
-    return __hiloint2double((k + 1023) << 20, 0);
+#define EMME_CX(i) c_cexp[i]
 #else
-    return ldexp(1.0, k);
+#define EMME_CX(i) h_cexp[i]
+#endif
+
+EMME_HD int hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int)(b >> 32);
+#endif
+}
+EMME_HD int lo_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int)(b & 0xffffffffLL);
+#endif
+}
+EMME_HD double from_words(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    const long long b = ((long long)hi << 32) | (unsigned int)lo;
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
 #endif
 }
 
@@ -356,49 +422,55 @@ EMME_HD cplx cexp_lib(double a, double b) {
 }
 
 EMME_HD cplx cexp_lean(double a, double b) {
-    if (fabs(b) < 524288.0 && fabs(a) < 700.0) {
-        const double MAGIC = 6755399441055744.0;       // 1.5 * 2^52: round-to-nearest-integer trick
-        // ---- sin b, cos b ----
-        const double qd = fma(b, 6.36619772367581382433e-01, MAGIC) - MAGIC;
-        double r = fma(-qd, 1.57079632673412561417e+00, b);       // pi/2, first 33 bits (exact product)
-        r = fma(-qd, 6.07710050630396597660e-11, r);              // next 33 bits
-        r = fma(-qd, 2.02226624879595063154e-21, r);              // tail
+    // |b| < 2^19 and |a| < 512, tested on the exponent fields (integer pipe)
+    if ((hi_word(b) & 0x7fffffff) < 0x41200000 && (hi_word(a) & 0x7fffffff) < 0x40800000) {
+        const double MAGIC = EMME_CX(30);
+        // ---- sin b, cos b: q = rint(b*2/pi) sits in the low word of b*2/pi + 1.5*2^52 ----
+        const double qm = fma(b, EMME_CX(0), MAGIC);
+        const int q = lo_word(qm);
+        const double qd = qm - MAGIC;
+        double r = fma(-qd, EMME_CX(1), b);        // exact product (33-bit constant, |q| < 2^20)
+        r = fma(-qd, EMME_CX(2), r);
+        r = fma(-qd, EMME_CX(3), r);
         const double z = r * r;
-        double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-        ps = fma(z, ps, 2.75573137070700676789e-06);
-        ps = fma(z, ps, -1.98412698298579493134e-04);
-        ps = fma(z, ps, 8.33333333332248946124e-03);
-        ps = fma(z, ps, -1.66666666666666324348e-01);
+        double ps = fma(z, EMME_CX(4), EMME_CX(5));
+        ps = fma(z, ps, EMME_CX(6));
+        ps = fma(z, ps, EMME_CX(7));
+        ps = fma(z, ps, EMME_CX(8));
+        ps = fma(z, ps, EMME_CX(9));
         const double sn = fma(z * r, ps, r);
-        double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-        pc = fma(z, pc, -2.75573143513906633035e-07);
-        pc = fma(z, pc, 2.48015872894767294178e-05);
-        pc = fma(z, pc, -1.38888888888741095749e-03);
-        pc = fma(z, pc, 4.16666666666666019037e-02);
+        double pc = fma(z, EMME_CX(10), EMME_CX(11));
+        pc = fma(z, pc, EMME_CX(12));
+        pc = fma(z, pc, EMME_CX(13));
+        pc = fma(z, pc, EMME_CX(14));
+        pc = fma(z, pc, EMME_CX(15));
         const double hz = 0.5 * z, w = 1.0 - hz;
         const double cs = w + (((1.0 - w) - hz) + z * (z * pc));
-        const int q = (int)qd;
-        double s_ = (q & 1) ? cs : sn, c_ = (q & 1) ? sn : cs;
-        if (q & 2) s_ = -s_;
-        if ((q + 1) & 2) c_ = -c_;
-        // ---- exp a ----
-        const double kd = fma(a, 1.44269504088896338700e+00, MAGIC) - MAGIC;
-        double t = fma(-kd, 6.93147180369123816490e-01, a);       // ln2, first 33 bits
-        t = fma(-kd, 1.90821492927058770002e-10, t);
-        double pe = fma(t, 1.6059043836821613e-10, 2.08767569878681e-09);   // 1/13!, 1/12!
-        pe = fma(t, pe, 2.505210838544172e-08);
-        pe = fma(t, pe, 2.755731922398589e-07);
-        pe = fma(t, pe, 2.7557319223985893e-06);
-        pe = fma(t, pe, 2.48015873015873e-05);
-        pe = fma(t, pe, 1.984126984126984e-04);
-        pe = fma(t, pe, 1.388888888888889e-03);
-        pe = fma(t, pe, 8.333333333333333e-03);
-        pe = fma(t, pe, 4.1666666666666664e-02);
-        pe = fma(t, pe, 1.6666666666666666e-01);
+        // quadrant: swap for odd q, signs from bit 1 of q (sin) and of q+1 (cos), applied to the sign bits
+        const double s0 = (q & 1) ? cs : sn, c0 = (q & 1) ? sn : cs;
+        const double s_ = from_words(hi_word(s0) ^ ((q & 2) << 30), lo_word(s0));
+        const double c_ = from_words(hi_word(c0) ^ (((q + 1) & 2) << 30), lo_word(c0));
+        // ---- exp a = 2^k * exp(t), k = rint(a*log2 e), |t| <= ln2/2: Taylor to t^13 (4e-18) ----
+        const double km = fma(a, EMME_CX(16), MAGIC);
+        const int k = lo_word(km);
+        const double kd = km - MAGIC;
+        double t = fma(-kd, EMME_CX(17), a);
+        t = fma(-kd, EMME_CX(18), t);
+        double pe = fma(t, EMME_CX(19), EMME_CX(20));
+        pe = fma(t, pe, EMME_CX(21));
+        pe = fma(t, pe, EMME_CX(22));
+        pe = fma(t, pe, EMME_CX(23));
+        pe = fma(t, pe, EMME_CX(24));
+        pe = fma(t, pe, EMME_CX(25));
+        pe = fma(t, pe, EMME_CX(26));
+        pe = fma(t, pe, EMME_CX(27));
+        pe = fma(t, pe, EMME_CX(28));
+        pe = fma(t, pe, EMME_CX(29));
         pe = fma(t, pe, 0.5);
         pe = fma(t, pe, 1.0);
         pe = fma(t, pe, 1.0);
-        const double er = pe * two_to((int)kd);
+        // scale by 2^k on the exponent field (pe in [0.7, 1.42], |k| < 740: always a normal number)
+        const double er = from_words(hi_word(pe) + (k << 20), lo_word(pe));
         return mk(er * c_, er * s_);
     }
     return cexp_lib(a, b);
