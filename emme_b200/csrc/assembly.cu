@@ -194,7 +194,6 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
 #pragma unroll 1
         for (int j = 0; j <= 2 * H; ++j) {
             const int ni = (j + 1) >> 1;                       // node index 0..H
-            const double node = (j & 1) ? T.a[ni] : -T.a[ni];  // j = 0: -0*scale + mid = mid
             if (active) {
                 NodeConst nc;
                 if (pid >= 0) {
@@ -211,6 +210,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                     nc.icsq = e5.x;
                 } else {
                     // node position exactly as the reference forms it: scale*x + mid, no FMA
+                    const double node = (j & 1) ? T.a[ni] : -T.a[ni];  // j = 0: -0*scale + mid = mid
                     const double l = lane_state[LS_L * BLOCK], r = lane_state[LS_R * BLOCK];
                     const double mid = (r + l) / 2, scale = (r - l) / 2;
                     nc = node_const(rc, __dadd_rn(__dmul_rn(scale, node), mid));

@@ -179,7 +179,9 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     // exact root and floor of the rounded root differ only if |z| lies within an ulp of an integer.
     const double n2 = norm2(z);
 #if defined(__CUDA_ARCH__)
-    int n0 = (int)__fsqrt_rn((float)n2);
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"((float)n2));   // +-1 is repaired below
+    int n0 = (int)sq;
 #else
     int n0 = (int)sqrtf((float)n2);
 #endif
