@@ -100,11 +100,13 @@ __device__ __forceinline__ void scatter(const RunConst& rc, const PeerSet& A, in
 // of registers ([field][thread]: conflict-free): the pair constants of the integrand (7 doubles,
 // one load each per evaluation), the current interval and the running sum.  This is what lets five
 // CTAs (20 warps) stay resident per SM without spills (r1j).
-enum { PS_DV, PS_BETA1, PS_CL, PS_S, PS_TWO_OVER_S, PS_HB, PS_C1, PS_FIELDS };
+enum { PS_DV, PS_CL, PS_S, PS_TWO_OVER_S, PS_HB, PS_C1, PS_CA, PS_CB, PS_CAA, PS_FIELDS };
 struct PairSmem {
     const volatile double* p;     // &s_pair[0][threadIdx.x]
     __device__ __forceinline__ double f_Dv() const { return p[PS_DV * BLOCK]; }
-    __device__ __forceinline__ double f_beta1() const { return p[PS_BETA1 * BLOCK]; }
+    __device__ __forceinline__ double f_ca() const { return p[PS_CA * BLOCK]; }
+    __device__ __forceinline__ double f_cb() const { return p[PS_CB * BLOCK]; }
+    __device__ __forceinline__ double f_cA() const { return p[PS_CAA * BLOCK]; }
     __device__ __forceinline__ double f_cl() const { return p[PS_CL * BLOCK]; }
     __device__ __forceinline__ double f_s() const { return p[PS_S * BLOCK]; }
     __device__ __forceinline__ double f_two_over_s() const { return p[PS_TWO_OVER_S * BLOCK]; }
@@ -166,7 +168,9 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                         const PairConst c = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
                         volatile double* ps = &s_pair[0][threadIdx.x];
                         ps[PS_DV * BLOCK] = c.Dv;
-                        ps[PS_BETA1 * BLOCK] = c.beta1;
+                        ps[PS_CA * BLOCK] = c.ca;
+                        ps[PS_CB * BLOCK] = c.cb;
+                        ps[PS_CAA * BLOCK] = c.cA;
                         ps[PS_CL * BLOCK] = c.cl;
                         ps[PS_S * BLOCK] = c.s;
                         ps[PS_TWO_OVER_S * BLOCK] = c.two_over_s;
@@ -204,7 +208,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                                   e4 = __ldg(e + 4), e5 = __ldg(e + 5);
                     nc.taut = mk(e0.x, e0.y);
                     nc.itaut = mk(e1.x, e1.y);
-                    nc.it2 = mk(e2.x, e2.y);
+                    nc.h = mk(e2.x, e2.y);
                     nc.M = mk(e3.x, e3.y);
                     nc.pj = mk(e4.x, e4.y);
                     nc.icsq = e5.x;

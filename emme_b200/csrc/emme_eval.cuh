@@ -92,7 +92,7 @@ struct RunConst {
     double kappa_pref;  // (q*R)/(vt*sqrt(2*pi))         (src/Parameters.cpp:182-183)
     double ke1_pref;    // (q*R)/(2*vt*tau)              (src/Parameters.cpp:196)
     double ke2_pref;    // (q*q*R*R)/(2*vt*vt*tau)       (src/Parameters.cpp:200)
-    double vt_over_qR_num;  // unused placeholder keeps layout stable
+    double a0;          // Re(omega) - omega_s_i*(1 - 1.5*eta_i): constant part of i0_coef's numerator
     double omega_s_e;
     double eta_e;
     double diag_es;     // 1 + 1/tau                     (include/solver.h:443)
@@ -122,6 +122,9 @@ struct PairConst {
     double hb;      // 0.5*(b+b')
     double bsum;    // b+b'
     double c1;      // -omega_s_i*eta_i*s
+    double ca;      // Dv^2                      : nu^2 = ca/tau~^2
+    double cb;      // 0.5*beta1*Dv              : 0.5*beta1*nu = cb/tau~
+    double cA;      // omega_s_i*eta_i*Dv^2      : omega_s_i*eta_i*nu^2 = cA/tau~^2
     // accessors: eval_node is generic over where the pair constants live (this struct on the host
     // emulation, shared memory in the kernel -- see PairSmem in assembly.cu)
     EMME_HD double f_Dv() const { return Dv; }
@@ -131,6 +134,9 @@ struct PairConst {
     EMME_HD double f_two_over_s() const { return two_over_s; }
     EMME_HD double f_hb() const { return hb; }
     EMME_HD double f_c1() const { return c1; }
+    EMME_HD double f_ca() const { return ca; }
+    EMME_HD double f_cb() const { return cb; }
+    EMME_HD double f_cA() const { return cA; }
 };
 
 EMME_HD PairConst make_pair(const RunConst& rc, double eta, double etap, double g, double gp,
@@ -146,6 +152,9 @@ EMME_HD PairConst make_pair(const RunConst& rc, double eta, double etap, double 
     pc.bsum = b + bp;
     pc.hb = 0.5 * pc.bsum;
     pc.c1 = -rc.omega_s_i * rc.eta_i * pc.s;
+    pc.ca = pc.Dv * pc.Dv;
+    pc.cb = 0.5 * pc.beta1 * pc.Dv;
+    pc.cA = rc.wsi_etai * pc.ca;
     return pc;
 }
 
@@ -317,7 +326,7 @@ EMME_HD NodeTrig node_trig(double x) {
 struct NodeConst {
     cplx taut;    // tau~ = t*e
     cplx itaut;   // 1/tau~ = conj(e)/t
-    cplx it2;     // (1/tau~)^2
+    cplx h;       // -0.5*(1/tau~)^2
     cplx M;       // i*tau~*omega                       (:160)
     cplx pj;      // jacobian/tau~                      (:126-129, :174)
     double icsq;  // 1/cos^2 x                          (include/functions.h:317)
@@ -338,7 +347,7 @@ EMME_HD NodeConst node_const(const RunConst& rc, double x) {
     NodeConst nc;
     nc.taut = t * e;
     nc.itaut = it * conj(e);
-    nc.it2 = nc.itaut * nc.itaut;
+    nc.h = (-0.5) * (nc.itaut * nc.itaut);
     nc.M = mul_i(nc.taut * mk(rc.wr, rc.wi));
     nc.pj = nc.itaut * jacob;
     nc.icsq = nt.icsq;
@@ -489,13 +498,11 @@ EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeConst&
     const cplx z = pc.f_s() * il;                  // sqrt(b b')/lambda  (:135-136)
     const cplx zc = pc.f_two_over_s() * lambda;    // 2/z
     const cplx z4 = z.re < 0 ? z : -z;         // include/functions.h:407
-    // nu = qR*deta/(vt*tau~) = (D/vt)/tau~   (:140)
-    const double Dv = pc.f_Dv();
-    const cplx nu = Dv * nc.itaut;
-    const cplx nu2 = (Dv * Dv) * nc.it2;
-    // log of the exponential factor (:157-164); 2 + i*beta1/nu == 2*lambda
-    const double hb = pc.f_hb();
-    const cplx L = (-0.5) * nu2 + (0.5 * pc.f_beta1()) * mk(nu.im, -nu.re) + nc.M - hb * il;
+    // log of the exponential factor (:157-164) with nu = Dv/tau~ (:140) and 2 + i*beta1/nu == 2*lambda:
+    //   -nu^2/2 - i*beta1*nu/2 + i*tau~*omega - (b+b')/(2*lambda)  =  ca*h + cb*(-i/tau~) + M - hb/lambda
+    const double hb = pc.f_hb(), ca = pc.f_ca(), cb = pc.f_cb();
+    const cplx L = mk(fma(ca, nc.h.re, fma(cb, nc.itaut.im, fma(-hb, il.re, nc.M.re))),
+                      fma(ca, nc.h.im, fma(-cb, nc.itaut.re, fma(-hb, il.im, nc.M.im))));
     const cplx arg = L - z4;
     if (arg.re < -40.) return mk(0., 0.);      // safe_exp underflow guard (:167-173)
 
@@ -505,8 +512,9 @@ EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeConst&
     // i0_coef*y0 + i1_coef*y1 (:142-151) with pow(lambda, -3.) = il^3 factored as il * il^2:
     //   i0 = il*(A + B*il^2),  i1 = il*(c1*il^2),  A = omega - omega_s_i*inner,  B = wsi_etai*(hb - lambda)
     const cplx il2 = il * il;
-    const cplx inner = mk(1.0 + rc.eta_i * (0.5 * nu2.re - 1.5), rc.eta_i * (0.5 * nu2.im));
-    const cplx A = mk(rc.wr, rc.wi) - rc.omega_s_i * inner;
+    //   A = omega - omega_s_i*(1 + eta_i*(nu^2/2 - 1.5)) = a0 + cA*h  (+ i Im omega)
+    const double cA = pc.f_cA();
+    const cplx A = mk(fma(cA, nc.h.re, rc.a0), fma(cA, nc.h.im, rc.wi));
     const cplx B = rc.wsi_etai * (mk(hb, 0.) - lambda);
     const cplx S = (A + B * il2) * y0 + (pc.f_c1() * il2) * y1;
 
@@ -517,8 +525,11 @@ EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeConst&
 #endif
 
     cplx pw = nc.pj;                           // nu^m / tau~ * jacobian   (:174)
-    if (m >= 1) pw = pw * nu;
-    if (m >= 2) pw = pw * nu;
+    if (m >= 1) {
+        const cplx nu = pc.f_Dv() * nc.itaut;
+        pw = pw * nu;
+        if (m >= 2) pw = pw * nu;
+    }
     // f = pw * se * il * S / mu, 1/mu = conj(mu)/|mu|^2 with the real factor applied last
     const cplx f = (pw * se) * ((il * S) * conj(mu));
     const double sc = nc.icsq * rcp_pos(norm2(mu));

@@ -25,7 +25,6 @@ inline RunConst make_run_const(const emme_params& p, int npoints, double wr, dou
     rc.kappa_pref = (p.q * p.R) / (p.vt * std::sqrt((2.0 * M_PI)));
     rc.ke1_pref = (p.q * p.R) / (2.0 * p.vt * p.tau);
     rc.ke2_pref = (p.q * p.q * p.R * p.R) / (2.0 * p.vt * p.vt * p.tau);
-    rc.vt_over_qR_num = 0.0;
     rc.omega_s_e = p.omega_s_e;
     rc.eta_e = p.eta_e;
     rc.diag_es = 1.0 + 1.0 / p.tau;
@@ -40,6 +39,7 @@ inline RunConst make_run_const(const emme_params& p, int npoints, double wr, dou
     rc.dx = p.dx;
     rc.wr = wr;
     rc.wi = wi;
+    rc.a0 = wr - p.omega_s_i * (1.0 - 1.5 * p.eta_i);
     rc.omi = -std::copysign(1.0, wr);
     rc.maxdepth = p.integration_iteration_limit;
     rc.order = p.integration_start_points;
