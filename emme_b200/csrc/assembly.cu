@@ -22,7 +22,14 @@
 //     spill area sized for the contract "depth <= integration_iteration_limit";
 //   * persistent grid; at every panel boundary the idle lanes of a warp (finished integrals)
 //     refill TOGETHER from a global atomic counter once at least `refill_min` of them are idle,
-//     so a warp always consists of a few cohorts of consecutive items.
+//     so a warp always consists of a few cohorts of consecutive items;
+//   * everything an evaluation needs that does not depend on the pair (eta, eta') -- the contour
+//     rotation, its jacobian, i*tau~*omega -- comes from a table of the first bisection levels that
+//     node_table_kernel rebuilds at the start of every assembly (NodeConst, emme_eval.cuh);
+//   * the kernel is ISSUE-SLOT bound (an FP64 instruction occupies a scheduler for two cycles,
+//     nothing issues in its shadow), so per-lane state that is only touched at
+//     item or panel boundaries lives in shared memory and the evaluation is written for the
+//     smallest weighted instruction count.
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -2,18 +2,23 @@
 //
 // Replaces the LAPACK call of EigenSolver::newtonTraceSecantIteration
 // (reference include/solver.h:129-140): zsysv solves A X = A' for dim right-hand sides and
-// the step is delta = -1/trace(X).  Here:
-//   1. blocked right-looking LU with partial pivoting of W = A (row-major complex128), the
-//      elimination applied on the fly to B = A' (augmented system), so the forward
-//      substitution Y = L^-1 P B costs no extra pass;
-//      - panel (dim-k0 rows x NB columns): ONE cooperative kernel per panel, one thread per
-//        matrix row holding its NB panel entries in registers, one grid barrier per column
-//        (the block-local pivot candidate travels with its whole row, so a second barrier
-//        for "publish the pivot row" is not needed); row interchanges are implicit
-//        (threads track their row's position) and materialise when rows are written back;
+// the step is delta = -1/trace(X).  Three paths, chosen by capi.cu:
+//   symmetric path (launch_trace_sym, second half of this file) -- EMME's matrix is complex
+//      symmetric and diagonally strong: A = L D L^T without interchanges, M = L^-1 carried through
+//      the elimination, trace(A^-1 A') = sum_ij (M^T D^-1 M)_ij A'_ji contracted tile by tile.
+//      4 dim^3 flops; symmetry and the partial-pivoting criterion are verified on the device;
+//   LU paths (launch_trace_solve) -- the fallback for anything else:
+//   1. blocked right-looking LU of W = A (row-major complex128), the elimination applied on the
+//      fly to B = A' (augmented system), so the forward substitution Y = L^-1 P B costs no
+//      extra pass;
+//      - panels: optimistic (no interchanges, verified against the partial-pivoting criterion)
+//        or pivoting (one thread per matrix row holding its NB panel entries in registers, one
+//        cluster/grid barrier per column; the block-local pivot candidate travels with its
+//        whole row; row interchanges are implicit and materialise when rows are written back);
 //      - one fused kernel applies the interchanges to the other columns of W and to B and
 //        solves the NB x NB unit-lower triangle for the block row;
-//      - trailing update: register-tiled complex DGEMM (DFMA), K = NB.
+//      - trailing update: complex GEMM on the FP64 tensor cores (DMMA.8x8x4), 64 x 64 tiles,
+//        3-stage cp.async ring.
 //   2. blocked back substitution X = U^-1 Y restricted to the LOWER triangle of X -- the
 //      trace needs X_ii only, and X_lc (l >= c) depends on nothing above the diagonal -- which
 //      halves this phase;

@@ -6,8 +6,9 @@
 // recurrence of util::bessel_i_alter_helper (include/functions.h:381-408) inlined.
 //
 // This is NOT a transcription: everything that depends only on the pair (eta, eta') is
-// hoisted into PairConst, divisions by complex numbers are replaced by one reciprocal of
-// lambda and one of mu, and two algebraic identities remove work per node:
+// hoisted into PairConst, everything that depends only on the node (and omega) into NodeConst,
+// divisions by complex numbers are replaced by one reciprocal of lambda and one of mu, and two
+// algebraic identities remove work per node:
 //     2 + i*beta_1/nu  ==  2*lambda            (nu = qR*deta/(vt*tau~))
 //     1/tau~           ==  conj(e)/t           (tau~ = t*e, |e| = 1)
 // so results agree with the reference to rounding (a few ulp per factor), not bit-for-bit.
