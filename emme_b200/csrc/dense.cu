@@ -706,22 +706,28 @@ __device__ __forceinline__ z_t zrecip_fast(z_t a) {
 // One launch per NB-wide panel [k0, k0+jb).  Small code, no per-thread register rows (the
 // unrolled one-thread-per-row elimination of panel_nopiv_kernel is instruction-fetch bound: every
 // instruction executes once), tensor cores for the two block products:
-//   1. every CTA requests its 64 x 32 (or 32 x 64) operand tile with cp.async, then factors the
-//      jb x jb diagonal block redundantly in shared memory while the tile is in flight: all 128
-//      threads, thread (row i = t/4, columns k = t%4 + 4e), one barrier per pivot.  The identity is
-//      carried along (Gauss-Jordan on the lower part), so the block ends as L11 \ U11 in sD and
-//      Mi = L11^-1 (explicit unit diagonal, zeros above) in sM;
+//   1. every CTA loads the jb x jb diagonal block, requests its operand tile with cp.async and
+//      factors the block redundantly in shared memory while the tile is in flight: all 128
+//      threads, thread (row i = t/4, columns k = t%4 + 4e), one barrier per pivot, no branches on
+//      the pivot chain.  In-place Gauss-Jordan: the identity is carried along in the part of the
+//      block the elimination has already left, every row i > c is updated over ALL columns
+//      (a_ik -= l a_ck; column c itself becomes -l), so the block ends as
+//      Mi = L11^-1 (strictly lower) \ U11 (diagonal and above); L11 goes to a second array;
 //   2. row CTAs [0, n_row_ctas): T = A21 Mi^T on the FP64 tensor cores.  U11 = D L11^T (symmetry)
 //      makes T[r][c] the entry a_rc just before column c is eliminated, hence
 //         L[r, c] = T[r][c] / u_cc,   U[k0+c, r] = T[r][c]   (U12 = D L21^T: no block-row solve)
 //      and |T[r][c]| <= tau |u_cc| is the partial-pivoting check;
 //   3. column CTAs: rows k0..ke of Y <- Mi Y (the identity carried along: rows k0..ke of
-//      M = L^-1 become final), 64 columns of Y per CTA.
-constexpr int PS_ROWS = 64;                       // rows (row role) / columns (Y role) per CTA
-constexpr int PS_LD = NB + 4;                     // stride of sD, sM, row tile: 4 (mod 8) elements
-constexpr int PS_LDY = PS_ROWS + 2;               // stride of the Y tile: 2 (mod 8) elements
-constexpr int PS_TILE = PS_ROWS * PS_LD > NB * PS_LDY ? PS_ROWS * PS_LD : NB * PS_LDY;
-constexpr size_t PS_SMEM_BYTES = sizeof(z_t) * (2 * NB * PS_LD + PS_TILE) + sizeof(z_t) * NB + sizeof(double) * NB;
+//      M = L^-1 become final).
+// A CTA owns `tile` = 16, 32 or 64 rows (row role) or columns (Y role): small systems get small
+// tiles so that the products, which run at one SM's tensor rate, spread over more SMs.
+// A zero or badly scaled pivot raises the flag like a failed pivoting test: the caller repeats the
+// step with the pivoting LU, which reports exact singularity (info) properly.
+constexpr int PS_ROWS = 64;                       // largest tile
+constexpr int PS_LD = NB + 4;                     // stride of sG, sL, sM, row tile: 4 (mod 8) elements
+constexpr int PS_LDY_MAX = PS_ROWS + 2;           // stride of the Y tile: tile + 2 = 2 (mod 8) elements
+constexpr int PS_TILE = PS_ROWS * PS_LD > NB * PS_LDY_MAX ? PS_ROWS * PS_LD : NB * PS_LDY_MAX;
+constexpr size_t PS_SMEM_BYTES = sizeof(z_t) * (3 * NB * PS_LD + PS_TILE) + sizeof(z_t) * NB + sizeof(double) * NB;
 
 #ifdef EMME_PS_CLOCKS
 __device__ long long g_ps_clocks[8];   // scratch/panel_bench.cu: phase boundaries of CTA 0
@@ -732,87 +738,111 @@ __device__ long long g_ps_clocks[8];   // scratch/panel_bench.cu: phase boundari
 
 __global__ void __launch_bounds__(128)
 panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int k0, int jb, int ycols,
-                 int n_row_ctas, double tau, int* __restrict__ flag, int* __restrict__ info) {
+                 int n_row_ctas, int tile, double tau, int* __restrict__ flag) {
     static_assert(NB == 32, "thread mapping of the diagonal-block factorisation");
     extern __shared__ __align__(16) unsigned char ps_smem_raw[];
-    z_t* sD = reinterpret_cast<z_t*>(ps_smem_raw);   // [NB][PS_LD]
-    z_t* sM = sD + NB * PS_LD;                        // [NB][PS_LD]
+    z_t* sG = reinterpret_cast<z_t*>(ps_smem_raw);   // [NB][PS_LD] Gauss-Jordan work array
+    z_t* sL = sG + NB * PS_LD;                        // [NB][PS_LD] L11
+    z_t* sM = sL + NB * PS_LD;                        // [NB][PS_LD] Mi with explicit unit diagonal
     z_t* sT = sM + NB * PS_LD;                        // operand tile
     z_t* sInv = sT + PS_TILE;                         // 1/u_cc
     double* sAbs = reinterpret_cast<double*>(sInv + NB);   // |u_cc| (cabs1)
     const int tid = threadIdx.x;
     PS_CLOCK(0);
     const bool row_role = (int)blockIdx.x < n_row_ctas;
-    const int r0 = jb + (int)blockIdx.x * PS_ROWS;                      // first row offset below k0
-    const int c0 = ((int)blockIdx.x - n_row_ctas) * PS_ROWS;            // first column of Y
-    // ---- request the operand tile first: it lands while the diagonal block is factored ----
+    const int r0 = jb + (int)blockIdx.x * tile;                         // first row offset below k0
+    const int c0 = ((int)blockIdx.x - n_row_ctas) * tile;               // first column of Y
+    const int ldy = tile + 2;
+    // ---- the diagonal block first (it is needed first), then the operand tile (cp.async) ----
+    const int gi = tid >> 2, gq = tid & 3;
+    z_t d8[NB / 4];
+#pragma unroll
+    for (int e = 0; e < NB / 4; ++e) {
+        const int k = gq + 4 * e;
+        d8[e] = (gi < jb && k < jb) ? W[(size_t)(k0 + gi) * ld + k0 + k] : make_double2(gi == k ? 1. : 0., 0.);
+    }
     if (row_role) {
-        // rows r0 .. r0+63 of the panel, 32 columns each (one 512-byte row per warp instruction)
-#pragma unroll 4
-        for (int it = 0; it < PS_ROWS / 4; ++it) {
-            const int rr = (tid >> 5) + 4 * it, cc = tid & 31;
+        // rows r0 .. r0+tile-1 of the panel, 32 columns each (one 512-byte row per warp instruction)
+        for (int rr = tid >> 5; rr < tile; rr += 4) {
+            const int cc = tid & 31;
             const bool ok = (k0 + r0 + rr < dim) && cc < jb;
             const z_t* src = ok ? W + (size_t)(k0 + r0 + rr) * ld + k0 + cc : W;
             cp_async16(sT + rr * PS_LD + cc, src, ok);
         }
     } else {
-#pragma unroll 4
-        for (int it = 0; it < NB / 2; ++it) {
-            const int kk = (tid >> 6) + 2 * it, nn = tid & 63;
+        // rows k0 .. k0+31 of Y, `tile` columns each
+        for (int e = tid; e < NB * tile; e += 128) {
+            const int kk = e / tile, nn = e - kk * tile;
             const bool ok = kk < jb && (c0 + nn < ycols);
             const z_t* src = ok ? Y + (size_t)(k0 + kk) * ld + c0 + nn : Y;
-            cp_async16(sT + kk * PS_LDY + nn, src, ok);
+            cp_async16(sT + kk * ldy + nn, src, ok);
         }
     }
     cp_async_commit();
-    for (int e = tid; e < NB * NB; e += 128) {
-        const int rr = e / NB, cc = e % NB;
-        sD[rr * PS_LD + cc] = (rr < jb && cc < jb) ? W[(size_t)(k0 + rr) * ld + k0 + cc] : make_double2(0., 0.);
-        sM[rr * PS_LD + cc] = make_double2(rr == cc ? 1. : 0., 0.);
-    }
+#pragma unroll
+    for (int e = 0; e < NB / 4; ++e) sG[gi * PS_LD + gq + 4 * e] = d8[e];
     __syncthreads();
     PS_CLOCK(1);
     int bad = 0;
     {
-        const int i = tid >> 2, q = tid & 3;
+        z_t* const rowi = sG + gi * PS_LD;
+        const bool in_block = gi < jb;
         for (int c = 0; c < jb; ++c) {
-            const z_t u = sD[c * PS_LD + c];
-            const double ua = fabs(u.x) + fabs(u.y);
-            const z_t inv = ua > 0.0 ? zrecip_fast(u) : make_double2(0., 0.);
-            if (tid == 0) {
-                sInv[c] = inv;
-                sAbs[c] = ua;
-                if (ua == 0.0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + c + 1);
-            }
-            const bool act = i > c && i < jb;
-            // Branch-free update of this thread's 8 entries of row i: columns k > c live in sD (the
-            // Schur complement), columns k <= c in sM (the identity carried along; sM[c][c] = 1 and
-            // sM[i][c] = 0 make column c come out as -l without a special case).  All 16 shared-memory
-            // loads are issued before the reciprocal is needed.
+            const z_t* rowc = sG + c * PS_LD;
+            // all shared-memory loads of the step are issued before the reciprocal is needed
+            const z_t u = rowc[c];
+            const z_t num = rowi[c];
             z_t x[NB / 4], pv[NB / 4];
 #pragma unroll
             for (int e = 0; e < NB / 4; ++e) {
-                const int k = q + 4 * e;
-                const z_t* src = k > c ? sD : sM;
-                x[e] = src[i * PS_LD + k];
-                pv[e] = src[c * PS_LD + k];
+                x[e] = rowi[gq + 4 * e];
+                pv[e] = rowc[gq + 4 * e];
             }
-            const z_t num = sD[i * PS_LD + c];
+            // column c: a_ic - l*1 with a_ic counted as 0 gives the carried identity's -l
+            const bool mine = gq == (c & 3);
+            const int ec = c >> 2;
+#pragma unroll
+            for (int e = 0; e < NB / 4; ++e)
+                if (mine && e == ec) {
+                    x[e] = make_double2(0., 0.);
+                    pv[e] = make_double2(1., 0.);
+                }
+            // 1/u: hardware seed + two Newton steps; a zero, non-finite or badly scaled pivot is
+            // reported through the flag (integer test on the exponent field)
+            const double n2 = u.x * u.x + u.y * u.y;
+            const unsigned ex = ((unsigned)__double2hiint(n2) >> 20) & 0x7ffu;
+            if (ex < 64u || ex > 1983u) bad = 1;
+            double d;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(d) : "d"(n2));
+            double er = fma(-n2, d, 1.0);
+            d = fma(d, er, d);
+            er = fma(-n2, d, 1.0);
+            d = fma(d, er, d);
+            const z_t inv = make_double2(u.x * d, -u.y * d);
+            const double ua = fabs(u.x) + fabs(u.y);
+            if (tid == 0) {
+                sInv[c] = inv;
+                sAbs[c] = ua;
+            }
             __syncwarp();   // the four threads of a row have read a_ic before one of them overwrites it
-            if (act) {
+            if (gi > c && in_block) {
                 const z_t l = zmul(num, inv);
-                if (q == 0 && fabs(num.x) + fabs(num.y) > tau * ua) bad = 1;
+                if (mine) {
+                    if (fabs(num.x) + fabs(num.y) > tau * ua) bad = 1;
+                    sL[gi * PS_LD + c] = l;
+                }
 #pragma unroll
                 for (int e = 0; e < NB / 4; ++e) zfms(x[e], l, pv[e]);
 #pragma unroll
-                for (int e = 0; e < NB / 4; ++e) {
-                    const int k = q + 4 * e;
-                    z_t* dst = k > c ? sD : sM;
-                    dst[i * PS_LD + k] = x[e];
-                }
-                if (q == (c & 3)) sD[i * PS_LD + c] = l;
+                for (int e = 0; e < NB / 4; ++e) rowi[gq + 4 * e] = x[e];
             }
             __syncthreads();
+        }
+        // clean copy of Mi for the tensor-core products: strictly lower part of sG, unit diagonal
+#pragma unroll
+        for (int e = 0; e < NB / 4; ++e) {
+            const int k = gq + 4 * e;
+            sM[gi * PS_LD + k] = k < gi ? rowi[k] : make_double2(k == gi ? 1. : 0., 0.);
         }
     }
     PS_CLOCK(2);
@@ -823,11 +853,13 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
         // the factored diagonal block goes back to W (L11 strictly below, U11 on and above the diagonal)
         for (int e = tid; e < NB * NB; e += 128) {
             const int rr = e / NB, cc = e % NB;
-            if (rr < jb && cc < jb) W[(size_t)(k0 + rr) * ld + k0 + cc] = sD[rr * PS_LD + cc];
+            if (rr < jb && cc < jb)
+                W[(size_t)(k0 + rr) * ld + k0 + cc] = cc < rr ? sL[rr * PS_LD + cc] : sG[rr * PS_LD + cc];
         }
     }
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
+    const int rg = tile >> 4;                     // 16-row groups per tile: 1, 2 or 4
     double acc_re[2][4][2], acc_im[2][4][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -837,35 +869,39 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
             acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
         }
     if (row_role) {
-        // T (64 x 32) = tile (64 x 32) * Mi^T: warp w owns rows 16w .. 16w+15
-#pragma unroll 2
+        // T (tile x 32) = tile * Mi^T: warp w owns rows 16 (w % rg).. and `rg` of the four 8-column blocks
+        const int wr = warp % rg, cb0 = (warp / rg) * rg;
         for (int k4 = 0; k4 < NB; k4 += 4) {
             z_t af[2], bf[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) af[i] = sT[(warp * 16 + i * 8 + g) * PS_LD + k4 + q];
+            for (int i = 0; i < 2; ++i) af[i] = sT[(wr * 16 + i * 8 + g) * PS_LD + k4 + q];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = sM[(j * 8 + g) * PS_LD + k4 + q];    // B[k][n] = Mi[n][k]
+            for (int j = 0; j < 4; ++j)
+                if (j < rg) bf[j] = sM[((cb0 + j) * 8 + g) * PS_LD + k4 + q];    // B[k][n] = Mi[n][k]
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const double nai = -af[i].y;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    dmma(acc_re[i][j], af[i].x, bf[j].x);
-                    dmma(acc_im[i][j], af[i].x, bf[j].y);
-                    dmma(acc_re[i][j], nai, bf[j].y);
-                    dmma(acc_im[i][j], af[i].y, bf[j].x);
+                    if (j < rg) {
+                        dmma(acc_re[i][j], af[i].x, bf[j].x);
+                        dmma(acc_im[i][j], af[i].x, bf[j].y);
+                        dmma(acc_re[i][j], nai, bf[j].y);
+                        dmma(acc_im[i][j], af[i].y, bf[j].x);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int r = r0 + warp * 16 + i * 8 + g;
+            const int r = r0 + wr * 16 + i * 8 + g;
             if (k0 + r >= dim) continue;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                if (j >= rg) continue;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int c = j * 8 + 2 * q + e;
+                    const int c = (cb0 + j) * 8 + 2 * q + e;
                     if (c >= jb) continue;
                     const z_t t = make_double2(acc_re[i][j][e], acc_im[i][j][e]);
                     if (fabs(t.x) + fabs(t.y) > tau * sAbs[c]) bad = 1;
@@ -875,24 +911,26 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
             }
         }
     } else {
-        // rows k0..ke of Y (32 x 64 tile) <- Mi * tile: warp w owns rows 16 (w&1).., columns 32 (w>>1)..
-        const int mb = warp & 1, nh = warp >> 1;
-#pragma unroll 2
+        // rows k0..ke of Y (32 x tile) <- Mi * tile: warp w owns rows 16 (w&1).. and `rg` 8-column blocks
+        const int mb = warp & 1, nb0 = (warp >> 1) * rg;
         for (int k4 = 0; k4 < NB; k4 += 4) {
             z_t af[2], bf[4];
 #pragma unroll
             for (int i = 0; i < 2; ++i) af[i] = sM[(mb * 16 + i * 8 + g) * PS_LD + k4 + q];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = sT[(k4 + q) * PS_LDY + nh * 32 + j * 8 + g];
+            for (int j = 0; j < 4; ++j)
+                if (j < rg) bf[j] = sT[(k4 + q) * ldy + (nb0 + j) * 8 + g];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const double nai = -af[i].y;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    dmma(acc_re[i][j], af[i].x, bf[j].x);
-                    dmma(acc_im[i][j], af[i].x, bf[j].y);
-                    dmma(acc_re[i][j], nai, bf[j].y);
-                    dmma(acc_im[i][j], af[i].y, bf[j].x);
+                    if (j < rg) {
+                        dmma(acc_re[i][j], af[i].x, bf[j].x);
+                        dmma(acc_im[i][j], af[i].x, bf[j].y);
+                        dmma(acc_re[i][j], nai, bf[j].y);
+                        dmma(acc_im[i][j], af[i].y, bf[j].x);
+                    }
                 }
             }
         }
@@ -902,9 +940,10 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
             if (m >= jb) continue;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                if (j >= rg) continue;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int n = c0 + nh * 32 + j * 8 + 2 * q + e;
+                    const int n = c0 + (nb0 + j) * 8 + 2 * q + e;
                     if (n >= ycols) continue;
                     Y[(size_t)(k0 + m) * ld + n] = make_double2(acc_re[i][j][e], acc_im[i][j][e]);
                 }
@@ -1427,9 +1466,11 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
         for (int k0 = K0; k0 < KE; k0 += NB) {
             const int jb = KE - k0 < NB ? KE - k0 : NB;
             const int ke = k0 + jb;
-            const int n_row = (dim - ke + PS_ROWS - 1) / PS_ROWS, n_col = (ke + PS_ROWS - 1) / PS_ROWS;
+            // tile = rows (columns of Y) per CTA: small systems get small tiles (more SMs share the products)
+            const int tile = dim <= 4736 ? 16 : (dim <= 9472 ? 32 : 64);
+            const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
             panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, ke, n_row,
-                                                                            g_tau, d_flag, d_info);
+                                                                            tile, g_tau, d_flag);
             ++nl;
             // inside the outer block: columns [ke, KE) of W below the panel, rows [ke, KE) of Y
             if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, ke, k0, jb);

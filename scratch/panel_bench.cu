@@ -25,14 +25,15 @@ int main(int argc, char** argv) {
     cudaMemset(info, 0, 4);
     gemm_setup();
     const int k0 = 0, jb = 32, ke = 32;
-    const int n_row = (dim - ke + PS_ROWS - 1) / PS_ROWS, n_col = (ke + PS_ROWS - 1) / PS_ROWS;
+    const int tile = dim <= 4736 ? 16 : (dim <= 9472 ? 32 : 64);
+    const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemcpy(W, h.data(), sizeof(double2) * dim * dim, cudaMemcpyHostToDevice);
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES>>>(W, Y, dim, dim, k0, jb, ke, n_row, 4.0, flag, info);
+        panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES>>>(W, Y, dim, dim, k0, jb, ke, n_row, tile, 4.0, flag);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
