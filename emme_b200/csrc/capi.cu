@@ -77,8 +77,8 @@ struct emme_solver {
     int null_optimistic = 1;
     int use_graph = 1;                // replay the optimistic dense step as a CUDA graph
     int use_sym = 1;                  // try the symmetric (L D L^T, explicit inverse) path first
-    cudaGraphExec_t dense_graph = nullptr, sym_graph = nullptr;
-    unsigned long long dense_graph_launches = 0, sym_graph_launches = 0;
+    cudaGraphExec_t dense_graph = nullptr, sym_graph = nullptr, qr_graph = nullptr;
+    unsigned long long dense_graph_launches = 0, sym_graph_launches = 0, qr_graph_launches = 0;
     unsigned long long pivot_fallbacks = 0, sym_steps = 0;
     int* d_flag = nullptr;
     size_t bytes() const { return sizeof(double) * 2 * (size_t)dim * dim; }
@@ -166,6 +166,7 @@ int emme_destroy(emme_solver* s) {
     cudaFree(s->d_flag);
     if (s->dense_graph) cudaGraphExecDestroy(s->dense_graph);
     if (s->sym_graph) cudaGraphExecDestroy(s->sym_graph);
+    if (s->qr_graph) cudaGraphExecDestroy(s->qr_graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_copy_src) cudaEventDestroy(s->ev_copy_src);
@@ -597,8 +598,13 @@ static int qr_delta(emme_solver* s, zc* delta) {
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, s->stream));
     CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
-    CU(emme::launch_qr_step(s->W, s->Ad, s->dim, s->d_qr_ws, s->d_qr_out, s->d_info, s->stream,
-                            &s->launches));
+    // 3*dim + 4 short launches on fixed buffers: captured once, replayed (launch bound otherwise)
+    {
+        int rc = replay_graph(s, &s->qr_graph, &s->qr_graph_launches, [&](unsigned long long* nl) {
+            return emme::launch_qr_step(s->W, s->Ad, s->dim, s->d_qr_ws, s->d_qr_out, s->d_info, s->stream, nl);
+        });
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(e1, s->stream));
     double out[4];
     int info = 0;

@@ -29,7 +29,7 @@ typedef double2 z_t;
 namespace {
 
 constexpr int QT = 1024;          // threads of the single-CTA kernels
-constexpr int CHUNK = 128;        // rows per CTA in the two grid kernels
+constexpr int CHUNK = 128;        // most rows per CTA in the two grid kernels (32 on small systems)
 constexpr int COLS = 128;         // columns per CTA (one thread per column: coalesced along rows)
 
 __device__ __forceinline__ z_t zmul(z_t a, z_t b) {
@@ -166,16 +166,18 @@ qr_pivot_kernel(z_t* __restrict__ A, int n, int i, double* __restrict__ vn1, dou
 
 // Step i, part 2: gpart[chunk][j] = sum over the chunk's rows r of conj(v_r) A[r][j], j > i.
 __global__ void __launch_bounds__(COLS)
-qr_vta_kernel(const z_t* __restrict__ A, int n, int i, const z_t* __restrict__ vbuf, z_t* __restrict__ gpart) {
+qr_vta_kernel(const z_t* __restrict__ A, int n, int i, int chunk, const z_t* __restrict__ vbuf,
+              z_t* __restrict__ gpart) {
     __shared__ z_t sv[CHUNK];
     const int j = i + 1 + blockIdx.x * COLS + threadIdx.x;
-    const int r0 = i + blockIdx.y * CHUNK;
-    for (int k = threadIdx.x; k < CHUNK; k += COLS)
+    const int r0 = i + blockIdx.y * chunk;
+    for (int k = threadIdx.x; k < chunk; k += COLS)
         sv[k] = (r0 + k < n) ? vbuf[r0 + k - i] : make_double2(0., 0.);
     __syncthreads();
     if (j >= n) return;
     double gx = 0., gy = 0.;
-    const int rend = r0 + CHUNK < n ? r0 + CHUNK : n;
+    const int rend = r0 + chunk < n ? r0 + chunk : n;
+#pragma unroll 8
     for (int r = r0; r < rend; ++r) {
         const z_t a = A[(size_t)r * n + j];
         const z_t v = sv[r - r0];
@@ -191,13 +193,13 @@ qr_vta_kernel(const z_t* __restrict__ A, int n, int i, const z_t* __restrict__ v
 // temp2 <= sqrt(eps): the norm must be recomputed (flag: vn1_j = -1, done by the next
 // qr_pivot_kernel); otherwise vn1_j *= sqrt(temp).
 __global__ void __launch_bounds__(COLS)
-qr_update_kernel(z_t* __restrict__ A, int n, int i, const z_t* __restrict__ vbuf, const z_t* __restrict__ gpart,
-                 int nchunk, const z_t* __restrict__ tau, double* __restrict__ vn1,
-                 const double* __restrict__ vn2, int* __restrict__ nflag) {
+qr_update_kernel(z_t* __restrict__ A, int n, int i, int chunk, const z_t* __restrict__ vbuf,
+                 const z_t* __restrict__ gpart, int nchunk, const z_t* __restrict__ tau,
+                 double* __restrict__ vn1, const double* __restrict__ vn2, int* __restrict__ nflag) {
     __shared__ z_t sv[CHUNK];
     const int j = i + 1 + blockIdx.x * COLS + threadIdx.x;
-    const int r0 = i + blockIdx.y * CHUNK;
-    for (int k = threadIdx.x; k < CHUNK; k += COLS)
+    const int r0 = i + blockIdx.y * chunk;
+    for (int k = threadIdx.x; k < chunk; k += COLS)
         sv[k] = (r0 + k < n) ? vbuf[r0 + k - i] : make_double2(0., 0.);
     __syncthreads();
     if (j >= n) return;
@@ -209,7 +211,8 @@ qr_update_kernel(z_t* __restrict__ A, int n, int i, const z_t* __restrict__ vbuf
     }
     const z_t ct = zconj(tau[i]);
     const z_t f = zmul(ct, make_double2(gx, gy));          // conj(tau) g_j
-    const int rend = r0 + CHUNK < n ? r0 + CHUNK : n;
+    const int rend = r0 + chunk < n ? r0 + chunk : n;
+#pragma unroll 4
     for (int r = r0; r < rend; ++r) {
         const z_t v = sv[r - r0];
         z_t a = A[(size_t)r * n + j];
@@ -362,8 +365,12 @@ qr_apply_qh_kernel(const z_t* __restrict__ QR, int n, const z_t* __restrict__ ta
 
 }  // namespace
 
+// rows per CTA: short loops (more CTAs, fewer dependent memory round trips) while the step is
+// latency bound, long ones once it is bandwidth bound
+static int qr_chunk(int n) { return n <= 2048 ? 32 : CHUNK; }
+
 size_t qr_workspace_bytes(int n) {
-    const size_t nchunk = (n + CHUNK - 1) / CHUNK;
+    const size_t nchunk = (n + qr_chunk(n) - 1) / qr_chunk(n);
     // vn1, vn2 | tau, vbuf, x, vfull, t | gpart | jpvt | nflag
     return sizeof(double) * 2 * n + sizeof(z_t) * 5 * (size_t)n + sizeof(z_t) * nchunk * n + sizeof(int) * n +
            512;
@@ -378,7 +385,8 @@ cudaError_t launch_qr_step(void* Wv, const void* Bv, int n, void* workspace, voi
         p += (bytes + 15) / 16 * 16;
         return q;
     };
-    const int nchunk_max = (n + CHUNK - 1) / CHUNK;
+    const int chunk = qr_chunk(n);
+    const int nchunk_max = (n + chunk - 1) / chunk;
     double* vn1 = (double*)take(sizeof(double) * n);
     double* vn2 = (double*)take(sizeof(double) * n);
     z_t* tau = (z_t*)take(sizeof(z_t) * n);
@@ -401,10 +409,10 @@ cudaError_t launch_qr_step(void* Wv, const void* Bv, int n, void* workspace, voi
         ++nl;
         const int ncols = n - i - 1;
         if (ncols > 0) {
-            const int nchunk = (n - i + CHUNK - 1) / CHUNK;
+            const int nchunk = (n - i + chunk - 1) / chunk;
             dim3 g((ncols + COLS - 1) / COLS, nchunk);
-            qr_vta_kernel<<<g, COLS, 0, stream>>>(W, n, i, vbuf, gpart);
-            qr_update_kernel<<<g, COLS, 0, stream>>>(W, n, i, vbuf, gpart, nchunk, tau, vn1, vn2, nflag);
+            qr_vta_kernel<<<g, COLS, 0, stream>>>(W, n, i, chunk, vbuf, gpart);
+            qr_update_kernel<<<g, COLS, 0, stream>>>(W, n, i, chunk, vbuf, gpart, nchunk, tau, vn1, vn2, nflag);
             nl += 2;
         }
     }

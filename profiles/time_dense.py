@@ -10,7 +10,7 @@ p, _ = inp.params()
 kind = "dom"
 args = []
 for a in sys.argv[1:]:
-    if a in ("dom", "piv", "sym"):
+    if a in ("dom", "piv", "sym", "qr"):
         kind = a
     else:
         args.append(int(a))
@@ -19,16 +19,16 @@ for n in args or [1024]:
     A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * (0.5 / np.sqrt(n)) + 2 * np.eye(n)
     if kind == "piv":
         A[::7] *= 0.01          # badly scaled rows: partial pivoting must interchange
-    if kind == "sym":
+    if kind in ("sym", "qr"):
         A = (A + A.T) / 2       # complex symmetric like EMME's matrices: symmetric path of kernel 2
     B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     s = EigenSolver(p, n, np.linspace(-1, 1, n), np.zeros(n), np.ones(n))
     ms = []
     for _ in range(4):
-        d = s.trace_delta(A, B)
+        d = s.qr_delta(A, B) if kind == "qr" else s.trace_delta(A, B)
         ms.append(s.stats()["dense_ms"])
     err = None
-    if n <= 2048:
+    if n <= 2048 and kind != "qr":
         ref = -1.0 / np.trace(np.linalg.solve(A, B))
         err = abs(d - ref) / abs(ref)
     fl = s.stats()["dense_flops"]
