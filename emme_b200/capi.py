@@ -38,6 +38,17 @@ class EmmeStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class EmmePicParams(C.Structure):
+    """struct emme_pic_params"""
+    _fields_ = [(n, C.c_double) for n in
+                ("q", "R", "vt", "tau", "shat", "b_theta", "length", "eta_i", "omega_s_i", "omega_d_bar",
+                 "water_bag_weight_vpara", "water_bag_weight_vperp")] + [
+        ("npoints", C.c_int), ("drift_center_transformation_switch", C.c_int)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # every symbol include/emme_b200.h declares: name -> (restype, argtypes)
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
@@ -84,6 +95,27 @@ PROTOTYPES = {
     "emme_input_get_string": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_int]),
     "emme_input_params": (C.c_int, [_vp, C.POINTER(EmmeParams), C.POINTER(C.c_int)]),
     "emme_input_tables": (C.c_int, [_vp, _dp, _dp, _dp]),
+    # row N4: PIC method
+    "emme_pic_load_markers": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, C.c_longlong, _dp, _dp, _dp, _dp]),
+    "emme_pic_create": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, _dp, _dp, _dp, _dp, C.c_int, C.POINTER(_vp)]),
+    "emme_pic_create_shard": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, _dp, _dp, _dp, _dp, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(_vp)]),
+    "emme_pic_destroy": (C.c_int, [_vp]),
+    "emme_pic_step": (C.c_int, [_vp, C.c_double, C.c_int]),
+    "emme_pic_steps_done": (C.c_long, [_vp]),
+    "emme_pic_marker_num": (C.c_long, [_vp]),
+    "emme_pic_current_field": (C.c_int, [_vp, _vp]),
+    "emme_pic_field_history": (C.c_int, [_vp, C.c_long, C.c_long, _vp]),
+    "emme_pic_markers": (C.c_int, [_vp, _dp, _dp]),
+    "emme_pic_extras": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "emme_pic_field_stats": (C.c_int, [_vp, C.c_long, C.c_long, _dp]),
+    "emme_pic_calculate_omega": (C.c_int, [_dp, C.c_long, C.c_double, _dp, _dp]),
+    "emme_pic_get_timing": (C.c_int, [_vp, _dp, C.POINTER(C.c_ulonglong)]),
+    "emme_pic_stream": (_vp, [_vp]),
+    "emme_pic_stage_begin": (C.c_int, [_vp, C.c_double, C.c_int]),
+    "emme_pic_stage_finish": (C.c_int, [_vp, C.c_int]),
+    "emme_pic_density_ptr": (_vp, [_vp]),
+    "emme_input_pic_params": (C.c_int, [_vp, C.POINTER(EmmePicParams), C.POINTER(C.c_long), C.POINTER(C.c_long), _dp]),
 }
 
 _lib = None

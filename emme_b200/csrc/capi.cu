@@ -16,6 +16,7 @@
 #include "../host/json.hpp"
 #include "../host/parameters.hpp"
 #include "assembly.h"
+#include "common.h"
 #include "dense.h"
 #include "qr.h"
 #include "run_const.h"
@@ -29,6 +30,8 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+
+int emme::capi_fail(int code, const std::string& msg) { return fail(code, msg); }
 
 #define CU(call)                                                                              \
     do {                                                                                      \
@@ -908,6 +911,30 @@ int emme_input_params(const emme_input* in, emme_params* p, int* npoints) {
         auto para = emme::Parameters::generate(in->json);
         if (p) *p = para->to_pod();
         if (npoints) *npoints = para->npoints;
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(EMME_E_INPUT, e.what());
+    }
+}
+
+int emme_input_pic_params(const emme_input* in, emme_pic_params* p, long* marker_per_cell,
+                          long* step_number, double* time_step) {
+    if (!in) return fail(-1, "null input");
+    try {
+        auto para = emme::Parameters::generate(in->json);
+        if (p) {
+            p->q = para->q; p->R = para->R; p->vt = para->vt; p->tau = para->tau;
+            p->shat = para->shat; p->b_theta = para->b_theta; p->length = para->length;
+            p->eta_i = para->eta_i; p->omega_s_i = para->omega_s_i; p->omega_d_bar = para->omega_d_bar;
+            p->water_bag_weight_vpara = para->water_bag_weight_vpara;
+            p->water_bag_weight_vperp = para->water_bag_weight_vperp;
+            p->npoints = para->npoints;
+            p->drift_center_transformation_switch = para->drift_center_transformation_switch ? 1 : 0;
+        }
+        // src/main.cpp:89,93-94
+        if (marker_per_cell) *marker_per_cell = (long)in->json.at("marker_per_cell").number();
+        if (step_number) *step_number = (long)in->json.at("step_number").number();
+        if (time_step) *time_step = in->json.at("time_step").number();
         return 0;
     } catch (const std::exception& e) {
         return fail(EMME_E_INPUT, e.what());

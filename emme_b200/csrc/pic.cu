@@ -1,0 +1,622 @@
+// pic.cu -- row N4: the reference's PIC method (`"method": "PIC"`, src/main.cpp:82-137) on the
+// GPU: PIC_State<double> + Integrator of include/solver_pic.h behind the emme_pic_* C ABI.
+//
+// The reference runs, per Runge-Kutta stage, three passes over the markers with a field solve
+// in between: put_velocity (include/solver_pic.h:76-135, one cyl_bessel_j(1, .) per marker),
+// update (:137-151) and solve_field (:251-354, one cyl_bessel_j(0, .) and one complex
+// exponential per marker, 256 thread-pool batches, a serial sum over the batches).
+//
+// Here a stage is ONE kernel (`pic_stage_kernel`), one marker per thread:
+//   gather   phi, dphi from the field (shared-memory copy, linear weights, :93-100)
+//   velocity vs = A phi + B dphi (+ the drift term without the pull-back transformation)
+//   combine  the stage's linear combination of velocities (Integrator::coef, :466-470: k0 has
+//            coefficient 0 after stage 0, so only k1 is ever stored)
+//   push     eta <- bound(eta + v_para h/(qR)), weight += v h  -- the reference's operation
+//            order, so eta is bit-identical to the reference's
+//   deposit  at the new eta: J0, J1 from ONE Miller backward recurrence (`bessel_j01`), the
+//            pull-back phase exp(-i omega_d_integral omega_dv) from one sincos, density
+//            j0 w dc_pb into per-CTA shared-memory cells (shared atomics), then one
+//            red.global.add.f64 per touched cell and CTA
+//   next     the marker's velocity coefficients A, B for the NEXT stage are formed now, while
+//            j0, dj0, dc_pb, omega_d(eta) are in registers: what crosses the field solve per
+//            marker is (eta, w, A, B) = 56 bytes instead of the reference's j0/dc_pb extras
+//            plus a second Bessel evaluation
+//   field    the last CTA to finish (ticket) turns the summed density into the new field
+//            (quasi-neutrality table, :349-351), clears the accumulators and, after stage 2,
+//            appends the field to the on-device history that the diagnostics read.
+// Three launches per Integrator::step, captured once per dt into a CUDA graph and replayed.
+//
+// Differences to the reference that are visible in the numbers: deposits are summed in a
+// different (and run-to-run varying) order, Bessel J comes from the Miller recurrence (abs. error
+// < 1e-15; libstdc++'s cyl_bessel_j is within 7e-15 of it) and the velocity is evaluated in
+// factored form; fields agree with the reference to ~1e-13 relative (tests/test_pic_gpu.py).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/emme_b200.h"
+#include "../host/json.hpp"
+#include "../host/parameters.hpp"
+#include "common.h"
+#include "pic_eval.cuh"
+
+namespace {
+
+using emme::d2;
+using emme::mk2;
+using emme::PicConst;
+
+struct PicDev {
+    PicConst k;
+    long n;
+    int nf;
+    int use_smem;
+    double* eta;
+    const double *vpar, *vperp, *pw;
+    d2 *w, *A, *B, *k1;
+    double* c;  // omega_d(eta) * omega_dv, only without the pull-back transformation
+    d2 *field, *dens;
+    const double* coef;
+    d2* hist;
+    unsigned* ticket;
+    unsigned long long* step;
+};
+
+__device__ __forceinline__ void deposit(const PicDev& d, d2* cells, double eta, d2 den) {
+    int idx;
+    double wt;
+    emme::pic_locate(d.k, eta, idx, wt);
+    const int i1 = (idx + 1 == d.nf) ? 0 : idx + 1;
+    const double w0 = 1.0 - wt;
+    atomicAdd(&cells[idx].x, den.x * w0);
+    atomicAdd(&cells[idx].y, den.y * w0);
+    atomicAdd(&cells[i1].x, den.x * wt);
+    atomicAdd(&cells[i1].y, den.y * wt);
+}
+
+// field = density * quasi-neutrality table (include/solver_pic.h:349-351); clears the density.
+__device__ __forceinline__ void finish_field(const PicDev& d, bool record) {
+    const unsigned long long slot = *d.step;
+    for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
+        const double2 raw = __ldcg(reinterpret_cast<const double2*>(&d.dens[i]));
+        const d2 v = mk2(raw.x, raw.y);
+        const double cf = d.coef[i];
+        const d2 f = mk2(v.x * cf, v.y * cf);
+        d.field[i] = f;
+        d.dens[i] = mk2(0.0, 0.0);
+        if (record) d.hist[slot * (unsigned long long)d.nf + i] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *d.ticket = 0;
+        if (record) *d.step = slot + 1;
+    }
+}
+
+__global__ void pic_field_kernel(PicDev d, int record) { finish_field(d, record != 0); }
+
+// First deposit-independent state: A = B = 0 (the reference's marker extras start with
+// j0 = dc_pb = 0, include/solver_pic.h:207-227, and the field with 0), c from the loaded eta.
+template <bool SWITCH>
+__global__ void pic_init_kernel(PicDev d) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < d.n; i += (long)gridDim.x * blockDim.x) {
+        d.A[i] = mk2(0.0, 0.0);
+        d.B[i] = mk2(0.0, 0.0);
+        d.k1[i] = mk2(0.0, 0.0);
+        if (!SWITCH) {
+            d.c[i] = emme::pic_initial_c(d.k, d.eta[i], d.vpar[i], d.vperp[i]);
+        }
+    }
+}
+
+// One Runge-Kutta stage for every marker.  h = coef[stage][stage+1] * dt; the stage's velocity
+// combination is v = k0 (stage 0), k1 (stage 1), c1 k1 + c2 k2 (stage 2).
+template <bool SWITCH, bool SMEM>
+__global__ void __launch_bounds__(256) pic_stage_kernel(PicDev d, int stage, double h, double c1,
+                                                        double c2, int finish) {
+    extern __shared__ d2 smem[];
+    d2* s_field = smem;
+    d2* s_dens = smem + d.nf;
+    __shared__ bool s_last;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
+            s_field[i] = d.field[i];
+            s_dens[i] = mk2(0.0, 0.0);
+        }
+        __syncthreads();
+    }
+    const d2* fld = SMEM ? s_field : d.field;
+    d2* cells = SMEM ? s_dens : d.dens;
+    const int nf = d.nf;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < d.n; i += (long)gridDim.x * blockDim.x) {
+        double eta = d.eta[i];
+        d2 w = d.w[i];
+        const d2 A = d.A[i], B = d.B[i];
+        const double vpar = d.vpar[i], vperp = d.vperp[i], pw = d.pw[i];
+        // gather + velocity of this stage (include/solver_pic.h:91-121)
+        d2 vs = emme::pic_velocity(d.k, fld, eta, A, B);
+        if (!SWITCH) {  // -weight omega_d omega_dv i (include/solver_pic.h:112-114)
+            const double c = d.c[i];
+            vs.x += c * w.y;
+            vs.y -= c * w.x;
+        }
+        d2 v = vs;
+        if (stage == 1) {
+            d.k1[i] = vs;
+        } else if (stage == 2) {
+            const d2 k1 = d.k1[i];
+            v = mk2(c1 * k1.x + c2 * vs.x, c1 * k1.y + c2 * vs.y);
+        }
+        // update (include/solver_pic.h:141-145), the reference's operation order for eta
+        eta = emme::pic_push(d.k, eta, vpar, h);
+        w.x = fma(v.x, h, w.x);
+        w.y = fma(v.y, h, w.y);
+        // deposit at the new position + coefficients of the next stage
+        d2 den, An, Bn;
+        double cn;
+        emme::pic_marker_at<SWITCH>(d.k, eta, vpar, vperp, pw, w, den, An, Bn, cn);
+        deposit(d, cells, eta, den);
+        d.eta[i] = eta;
+        d.w[i] = w;
+        d.A[i] = An;
+        d.B[i] = Bn;
+        if (!SWITCH) d.c[i] = cn;
+    }
+    if (SMEM) {
+        __syncthreads();
+        // rotate the start cell by CTA so that concurrent CTAs hit different L2 lines
+        const int rot = (int)(((long)blockIdx.x * 97) % nf);
+        for (int j = threadIdx.x; j < nf; j += blockDim.x) {
+            int i = j + rot;
+            if (i >= nf) i -= nf;
+            const d2 v = s_dens[i];
+            if (v.x != 0.0) atomicAdd(&d.dens[i].x, v.x);
+            if (v.y != 0.0) atomicAdd(&d.dens[i].y, v.y);
+        }
+    }
+    if (!finish) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(d.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        finish_field(d, stage == 2);
+    }
+}
+
+const double RK_COEF[4][4] = EMME_PIC_RK_COEF;
+
+}  // namespace
+
+struct emme_pic {
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    emme_pic_params p{};
+    long n = 0, n_total = 0, first = 0;
+    PicDev d{};
+    std::vector<double> h_pw, h_vpar, h_vperp, h_coef;  // host copies for emme_pic_extras
+    void* d_vpar = nullptr;
+    void* d_vperp = nullptr;
+    void* d_pw = nullptr;
+    void* d_coef = nullptr;
+    long hist_cap = 0;
+    long steps_done = 0;
+    int shard_count = 1;
+    int grid = 0;
+    size_t smem = 0;
+    cudaGraphExec_t graph = nullptr;
+    double graph_dt = 0;
+    int use_graph = 1;
+    double last_ms = 0;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+using emme::capi_fail;
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return capi_fail(EMME_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1));
+}
+
+int ensure_history(emme_pic* s, long steps_total) {
+    if (steps_total <= s->hist_cap) return 0;
+    long cap = s->hist_cap ? s->hist_cap : 256;
+    while (cap < steps_total) cap *= 2;
+    d2* nh = nullptr;
+    CU(dev_alloc(&nh, (size_t)cap * s->d.nf));
+    if (s->d.hist && s->steps_done > 0) {
+        CU(cudaMemcpyAsync(nh, s->d.hist, sizeof(d2) * (size_t)s->steps_done * s->d.nf,
+                           cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    if (s->d.hist) CU(cudaFree(s->d.hist));
+    s->d.hist = nh;
+    s->hist_cap = cap;
+    if (s->graph) {  // the captured launches hold the old pointer
+        cudaGraphExecDestroy(s->graph);
+        s->graph = nullptr;
+    }
+    return 0;
+}
+
+cudaError_t launch_stage(emme_pic* s, double dt, int stage, int finish) {
+    const double h = RK_COEF[stage][stage + 1] * dt;
+    const double c1 = RK_COEF[2][1], c2 = RK_COEF[2][2];
+    const bool sw = s->p.drift_center_transformation_switch != 0;
+    dim3 grid(s->grid), block(256);
+    if (s->d.use_smem) {
+        if (sw) pic_stage_kernel<true, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2, finish);
+        else pic_stage_kernel<false, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2, finish);
+    } else {
+        if (sw) pic_stage_kernel<true, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2, finish);
+        else pic_stage_kernel<false, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2, finish);
+    }
+    s->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int emme_pic_load_markers(const emme_pic_params* p, long n, long long seed, double* eta,
+                          double* v_para, double* v_perp, double* weight) {
+    if (!p) return capi_fail(-1, "null params");
+    if (n < 0) return capi_fail(-2, "negative marker count");
+    if (!eta || !v_para || !v_perp || !weight) return capi_fail(-4, "null output array");
+    // initialize_marker (include/solver_pic.h:186-205): same engine, same distributions, same
+    // order of draws per marker
+    std::mt19937 gen(seed < 0 ? std::random_device{}() : (unsigned)seed);
+    std::uniform_real_distribution<double> uniform_eta(-p->length, p->length);
+    std::uniform_real_distribution<double> uniform_w(0, 0.001);
+    std::normal_distribution<double> normal_vpara(0, p->vt / std::sqrt(p->water_bag_weight_vpara));
+    std::normal_distribution<double> normal_vperp(0, p->vt / std::sqrt(p->water_bag_weight_vperp));
+    for (long i = 0; i < n; ++i) {
+        eta[i] = uniform_eta(gen);
+        v_para[i] = normal_vpara(gen);
+        v_perp[i] = std::abs(normal_vperp(gen));
+        weight[2 * i] = uniform_w(gen);
+        weight[2 * i + 1] = 0.0;
+    }
+    return 0;
+}
+
+int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* eta,
+                          const double* v_para, const double* v_perp, const double* weight,
+                          int shard_index, int shard_count, int device, emme_pic** out) {
+    if (!p) return capi_fail(-1, "null params");
+    if (n_total <= 0) return capi_fail(-2, "marker count must be positive");
+    if (!eta) return capi_fail(-3, "null eta");
+    if (!v_para) return capi_fail(-4, "null v_para");
+    if (!v_perp) return capi_fail(-5, "null v_perp");
+    if (!weight) return capi_fail(-6, "null weight");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return capi_fail(-7, "bad shard");
+    if (!out) return capi_fail(-10, "null output handle");
+    if (p->npoints < 4) return capi_fail(-1, "npoints must be at least 4");
+    if (emme_device_count() <= 0)
+        return capi_fail(EMME_E_NO_DEVICE, "no CUDA device: emme_b200 has no CPU fallback");
+    CU(cudaSetDevice(device));
+    emme_pic* s = new emme_pic();
+    s->device = device;
+    s->p = *p;
+    s->n_total = n_total;
+    s->shard_count = shard_count;
+    // contiguous block of markers
+    const long per = n_total / shard_count, rem = n_total % shard_count;
+    s->first = shard_index * per + (shard_index < rem ? shard_index : rem);
+    s->n = per + (shard_index < rem ? 1 : 0);
+    const long n = s->n, f0 = s->first;
+    const int nf = p->npoints;
+    CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+
+    // initialize_marker_extras (include/solver_pic.h:207-238): p_weight normalised over ALL markers
+    std::vector<double> pw(n_total);
+    for (long i = 0; i < n_total; ++i) {
+        const double vp = v_para[i], vq = v_perp[i];
+        pw[i] = vq * std::exp(-(vp * vp * (1 - p->water_bag_weight_vpara) +
+                                vq * vq * (1 - p->water_bag_weight_vperp)) /
+                              (2 * p->vt * p->vt));
+    }
+    double sum = 0;
+    for (long i = 0; i < n_total; ++i) sum += pw[i];
+    const double inn = 2 * p->length / (sum);
+    s->h_pw.resize(n);
+    for (long i = 0; i < n; ++i) s->h_pw[i] = pw[f0 + i] * inn;
+    s->h_vpar.assign(v_para + f0, v_para + f0 + n);
+    s->h_vperp.assign(v_perp + f0, v_perp + f0 + n);
+    // cal_quasi_neutrality_coef (include/solver_pic.h:381-399)
+    const double cell_width = 2 * p->length / p->npoints;
+    s->h_coef.resize(nf);
+    for (int idx = 0; idx < nf; ++idx) {
+        const double b = p->b_theta * (1. + std::pow(p->shat * (idx * cell_width - p->length), 2));
+        const double g0 = std::cyl_bessel_i(0, b) * std::exp(-b);
+        s->h_coef[idx] = 1. / ((1. + 1. / p->tau - g0) * cell_width);
+    }
+
+    PicDev& d = s->d;
+    d.n = n;
+    d.nf = nf;
+    PicConst& k = d.k;
+    k.nf = nf;
+    k.L = p->length;
+    k.cw = cell_width;
+    k.inv_2cw = 1.0 / (2. * cell_width);
+    k.qR = p->q * p->R;
+    k.inv_qR = 1.0 / k.qR;
+    k.inv_vt = 1.0 / p->vt;
+    k.shat = p->shat;
+    k.b_theta = p->b_theta;
+    k.omega_d_bar = p->omega_d_bar;
+    k.omega_s_i = p->omega_s_i;
+    k.eta_i = p->eta_i;
+    k.inv_2vt2 = 1.0 / (2. * p->vt * p->vt);
+    double *dvpar, *dvperp, *dpw, *dcoef;
+    CU(dev_alloc(&d.eta, n));
+    CU(dev_alloc(&dvpar, n));
+    CU(dev_alloc(&dvperp, n));
+    CU(dev_alloc(&dpw, n));
+    CU(dev_alloc(&d.w, n));
+    CU(dev_alloc(&d.A, n));
+    CU(dev_alloc(&d.B, n));
+    CU(dev_alloc(&d.k1, n));
+    CU(dev_alloc(&d.c, p->drift_center_transformation_switch ? 1 : n));
+    CU(dev_alloc(&d.field, nf));
+    CU(dev_alloc(&d.dens, nf));
+    CU(dev_alloc(&dcoef, nf));
+    CU(dev_alloc(&d.ticket, 1));
+    CU(dev_alloc(&d.step, 1));
+    d.vpar = dvpar; d.vperp = dvperp; d.pw = dpw; d.coef = dcoef;
+    s->d_vpar = dvpar; s->d_vperp = dvperp; s->d_pw = dpw; s->d_coef = dcoef;
+    CU(cudaMemcpyAsync(d.eta, eta + f0, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(dvpar, v_para + f0, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(dvperp, v_perp + f0, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(dpw, s->h_pw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d.w, weight + 2 * f0, sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(dcoef, s->h_coef.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(d.field, 0, sizeof(d2) * nf, s->stream));
+    CU(cudaMemsetAsync(d.dens, 0, sizeof(d2) * nf, s->stream));
+    CU(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), s->stream));
+    CU(cudaMemsetAsync(d.step, 0, sizeof(unsigned long long), s->stream));
+
+    // launch geometry: field + density cells in shared memory when they fit
+    s->smem = sizeof(d2) * 2 * (size_t)nf;
+    d.use_smem = s->smem <= 200 * 1024;
+    const bool sw = p->drift_center_transformation_switch != 0;
+    int per_sm = 1;
+    if (d.use_smem) {
+        if (sw) {
+            CU(cudaFuncSetAttribute(pic_stage_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<true, true>, 256, s->smem));
+        } else {
+            CU(cudaFuncSetAttribute(pic_stage_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<false, true>, 256, s->smem));
+        }
+    } else {
+        s->smem = 0;
+        if (sw) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<true, false>, 256, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<false, false>, 256, 0));
+    }
+    if (per_sm < 1) per_sm = 1;
+    const long want = (n + 255) / 256;
+    const long cap = (long)s->sms * per_sm;
+    s->grid = (int)(want < cap ? want : cap);
+    if (const char* e = std::getenv("EMME_PIC_GRAPH")) s->use_graph = std::atoi(e);
+
+    const int ig = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    if (sw) pic_init_kernel<true><<<ig, 256, 0, s->stream>>>(d);
+    else pic_init_kernel<false><<<ig, 256, 0, s->stream>>>(d);
+    s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return 0;
+}
+
+int emme_pic_create(const emme_pic_params* p, long n_markers, const double* eta, const double* v_para,
+                    const double* v_perp, const double* weight, int device, emme_pic** out) {
+    return emme_pic_create_shard(p, n_markers, eta, v_para, v_perp, weight, 0, 1, device, out);
+}
+
+int emme_pic_destroy(emme_pic* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->graph) cudaGraphExecDestroy(s->graph);
+    PicDev& d = s->d;
+    cudaFree(d.eta); cudaFree(s->d_vpar); cudaFree(s->d_vperp); cudaFree(s->d_pw);
+    cudaFree(d.w); cudaFree(d.A); cudaFree(d.B); cudaFree(d.k1); cudaFree(d.c);
+    cudaFree(d.field); cudaFree(d.dens); cudaFree(s->d_coef); cudaFree(d.hist);
+    cudaFree(d.ticket); cudaFree(d.step);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+int emme_pic_step(emme_pic* s, double dt, int nsteps) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (nsteps < 0) return capi_fail(-3, "negative step count");
+    if (s->shard_count > 1)
+        return capi_fail(EMME_E_STATE, "sharded PIC state: use emme_pic_stage_begin/finish around the density exchange");
+    CU(cudaSetDevice(s->device));
+    if (int rc = ensure_history(s, s->steps_done + nsteps)) return rc;
+    if (s->use_graph && nsteps > 0 && (!s->graph || s->graph_dt != dt)) {
+        if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long before = s->launches;
+        cudaError_t e = cudaSuccess;
+        for (int st = 0; st < 3 && e == cudaSuccess; ++st) e = launch_stage(s, dt, st, 1);
+        s->launches = before;
+        cudaError_t e2 = cudaStreamEndCapture(s->stream, &g);
+        if (e != cudaSuccess) return capi_fail(EMME_E_CUDA, std::string("stage launch: ") + cudaGetErrorString(e));
+        CU(e2);
+        CU(cudaGraphInstantiate(&s->graph, g, 0));
+        CU(cudaGraphDestroy(g));
+        s->graph_dt = dt;
+    }
+    CU(cudaEventRecord(s->ev0, s->stream));
+    for (int k = 0; k < nsteps; ++k) {
+        if (s->use_graph) {
+            CU(cudaGraphLaunch(s->graph, s->stream));
+            s->launches += 3;
+        } else {
+            for (int st = 0; st < 3; ++st) CU(launch_stage(s, dt, st, 1));
+        }
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    s->steps_done += nsteps;
+    return 0;
+}
+
+int emme_pic_stage_begin(emme_pic* s, double dt, int stage) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (stage < 0 || stage > 2) return capi_fail(-3, "stage must be 0, 1 or 2");
+    CU(cudaSetDevice(s->device));
+    if (stage == 0)
+        if (int rc = ensure_history(s, s->steps_done + 1)) return rc;
+    CU(launch_stage(s, dt, stage, 0));
+    return 0;
+}
+
+int emme_pic_stage_finish(emme_pic* s, int stage) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (stage < 0 || stage > 2) return capi_fail(-2, "stage must be 0, 1 or 2");
+    CU(cudaSetDevice(s->device));
+    pic_field_kernel<<<1, 1024, 0, s->stream>>>(s->d, stage == 2);
+    s->launches++;
+    CU(cudaGetLastError());
+    if (stage == 2) s->steps_done++;
+    return 0;
+}
+
+void* emme_pic_density_ptr(emme_pic* s) { return s ? (void*)s->d.dens : nullptr; }
+void* emme_pic_stream(emme_pic* s) { return s ? (void*)s->stream : nullptr; }
+long emme_pic_steps_done(const emme_pic* s) { return s ? s->steps_done : -1; }
+long emme_pic_marker_num(const emme_pic* s) { return s ? s->n : -1; }
+
+int emme_pic_current_field(emme_pic* s, void* host_out) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (!host_out) return capi_fail(-2, "null output");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(host_out, s->d.field, sizeof(d2) * s->d.nf, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int emme_pic_field_history(emme_pic* s, long first, long count, void* host_out) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (first < 0 || count < 0 || first + count > s->steps_done) return capi_fail(-2, "step range outside the recorded history");
+    if (!host_out) return capi_fail(-4, "null output");
+    if (count == 0) return 0;
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(host_out, s->d.hist + (size_t)first * s->d.nf, sizeof(d2) * (size_t)count * s->d.nf,
+                       cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int emme_pic_markers(emme_pic* s, double* eta, double* weight) {
+    if (!s) return capi_fail(-1, "null handle");
+    CU(cudaSetDevice(s->device));
+    if (eta) CU(cudaMemcpyAsync(eta, s->d.eta, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (weight) CU(cudaMemcpyAsync(weight, s->d.w, sizeof(d2) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int emme_pic_extras(emme_pic* s, double* omega_dv, double* omega_st, double* p_weight, double* coef) {
+    if (!s) return capi_fail(-1, "null handle");
+    const emme_pic_params& p = s->p;
+    for (long i = 0; i < s->n; ++i) {
+        const double vp = s->h_vpar[i], vq = s->h_vperp[i];
+        if (omega_dv) omega_dv[i] = (vp * vp + .5 * vq * vq) / (2. * p.vt * p.vt);
+        if (omega_st)
+            omega_st[i] = p.omega_s_i * (1. + p.eta_i * ((vp * vp + vq * vq) / (2. * p.vt * p.vt) - 1.5));
+        if (p_weight) p_weight[i] = s->h_pw[i];
+    }
+    if (coef)
+        for (int i = 0; i < p.npoints; ++i) coef[i] = s->h_coef[i];
+    return 0;
+}
+
+int emme_pic_field_stats(emme_pic* s, long first, long count, double* stats3) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (!stats3) return capi_fail(-4, "null output");
+    const int nf = s->d.nf;
+    std::vector<std::complex<double>> h((size_t)count * nf);
+    if (int rc = emme_pic_field_history(s, first, count, h.data())) return rc;
+    for (long k = 0; k < count; ++k) {  // src/main.cpp:110-117
+        double real = 0, imag = 0, norm = 0;
+        for (int i = 0; i < nf; ++i) {
+            const std::complex<double> val = h[(size_t)k * nf + i];
+            real = real + std::real(val);
+            imag = imag + std::imag(val);
+            norm = norm + std::real(val * std::conj(val));
+        }
+        stats3[3 * k] = real / nf;
+        stats3[3 * k + 1] = imag / nf;
+        stats3[3 * k + 2] = std::sqrt(norm / nf);
+    }
+    return 0;
+}
+
+int emme_pic_calculate_omega(const double* stats3, long size, double dt, double* omega_re, double* omega_im) {
+    if (!stats3) return capi_fail(-1, "null stats");
+    if (size < 4) return capi_fail(-2, "need at least four steps");
+    if (!omega_re || !omega_im) return capi_fail(-4, "null output");
+    // util::calculate_omega (include/solver_pic.h:475-529)
+    const std::size_t n = (std::size_t)size / 2;
+    double t = 0, weighted_sum = 0, sum = 0;
+    for (std::size_t i = n; i < (std::size_t)size; ++i) {
+        const double val = std::log(stats3[3 * i + 2]);
+        weighted_sum += val * t;
+        sum += val;
+        t += dt;
+    }
+    const double gamma = 6 * (2 * weighted_sum - dt * sum * (n + 1)) / (dt * dt * n * (n * n - 1));
+    std::vector<double> real_log;
+    real_log.reserve(size - n);
+    for (std::size_t i = n; i < (std::size_t)size; ++i) real_log.push_back(std::log(std::abs(stats3[3 * i])));
+    std::vector<double> max_pts;
+    for (std::size_t i = 1; i + 1 < real_log.size(); ++i)
+        if (real_log[i] > real_log[i - 1] && real_log[i] > real_log[i + 1]) max_pts.push_back(i * dt);
+    double omega = 0;
+    if (max_pts.size() > 1) omega = M_PI * (max_pts.size() - 1) / (max_pts.back() - max_pts.front());
+    *omega_re = omega;
+    *omega_im = gamma;
+    return 0;
+}
+
+int emme_pic_get_timing(const emme_pic* s, double* last_step_call_ms, unsigned long long* launches) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (last_step_call_ms) *last_step_call_ms = s->last_ms;
+    if (launches) *launches = s->launches;
+    return 0;
+}
+
+}  // extern "C"

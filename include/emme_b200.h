@@ -182,6 +182,81 @@ int emme_input_get_string(const emme_input* in, const char* key, char* buf, int 
 int emme_input_params(const emme_input* in, emme_params* p, int* npoints);
 int emme_input_tables(const emme_input* in, double* eta, double* g, double* bi);
 
+/* ======================================================================================
+ * Row N4: the PIC method -- `"method": "PIC"`, solve_once_pic (src/main.cpp:82-137) on
+ * PIC_State<double> + Integrator (include/solver_pic.h).  Delta-f markers follow
+ * eta' = v_para/(qR) and carry a complex weight; every Runge-Kutta stage is
+ * put_velocity (include/solver_pic.h:76-135) + update (:137-151) + solve_field (:251-354),
+ * three stages per Integrator::step (:423-434).  On the device one kernel per stage does
+ * gather + velocity + push + Bessel/phase + deposit for every marker and the last CTA turns the
+ * deposited density into the new field.
+ * ====================================================================================== */
+
+/* The members of Parameters that PIC_State reads. */
+typedef struct emme_pic_params {
+    double q, R, vt, tau, shat, b_theta, length;
+    double eta_i, omega_s_i, omega_d_bar;            /* derived, src/Parameters.cpp:62-64 */
+    double water_bag_weight_vpara, water_bag_weight_vperp;
+    int npoints;                                      /* field cells                     */
+    int drift_center_transformation_switch;
+} emme_pic_params;
+
+typedef struct emme_pic emme_pic; /* opaque; owns device memory */
+
+/* Host: PIC_State::initialize_marker (include/solver_pic.h:186-205): n markers drawn from a
+ * std::mt19937 with the reference's distributions in the reference's draw order (eta, v_para,
+ * v_perp, weight).  seed < 0 seeds from std::random_device like the reference
+ * (include/solver_pic.h:356-359); a seed >= 0 makes the loading reproducible.  weight is n
+ * complex128 (re, im). */
+int emme_pic_load_markers(const emme_pic_params* p, long n, long long seed, double* eta,
+                          double* v_para, double* v_perp, double* weight);
+/* PIC_State constructor (include/solver_pic.h:62-67) from given markers (copied to the device):
+ * marker extras (:207-238), quasi-neutrality table (:381-399), zero field (:239-243). */
+int emme_pic_create(const emme_pic_params* p, long n_markers, const double* eta,
+                    const double* v_para, const double* v_perp, const double* weight, int device,
+                    emme_pic** out);
+int emme_pic_destroy(emme_pic* s);
+/* nsteps x Integrator::step(dt) (include/solver_pic.h:423-434).  The field after every step is
+ * kept on the device (the diagnostics of src/main.cpp:104-110 read it). */
+int emme_pic_step(emme_pic* s, double dt, int nsteps);
+long emme_pic_steps_done(const emme_pic* s);
+long emme_pic_marker_num(const emme_pic* s);
+/* PIC_State::current_field (include/solver_pic.h:170): npoints complex128 to host_out. */
+int emme_pic_current_field(emme_pic* s, void* host_out);
+/* The fields recorded after steps [first, first+count): count*npoints complex128, the byte
+ * stream solve_once_pic writes to eigenMatrics/ *.bin (src/main.cpp:106-108). */
+int emme_pic_field_history(emme_pic* s, long first, long count, void* host_out);
+/* Marker state for parity checks: eta (n doubles) and weight (n complex128); either may be NULL. */
+int emme_pic_markers(emme_pic* s, double* eta, double* weight);
+/* Derived tables: omega_dv, omega_st, p_weight (n doubles each), quasi-neutrality table
+ * (npoints doubles); any may be NULL. */
+int emme_pic_extras(emme_pic* s, double* omega_dv, double* omega_st, double* p_weight, double* coef);
+/* Per-step diagnostics of src/main.cpp:110-117 for steps [first, first+count): 3 doubles per
+ * step = {mean Re phi, mean Im phi, rms |phi|}, accumulated in the reference's order. */
+int emme_pic_field_stats(emme_pic* s, long first, long count, double* stats3);
+/* util::calculate_omega (include/solver_pic.h:475-529): growth rate from a least-squares line
+ * through log rms over the second half, frequency from the maxima of log |mean Re phi|. */
+int emme_pic_calculate_omega(const double* stats3, long n, double dt, double* omega_re, double* omega_im);
+/* CUDA-event time of the last emme_pic_step call and kernels launched so far. */
+int emme_pic_get_timing(const emme_pic* s, double* last_step_call_ms, unsigned long long* launches);
+void* emme_pic_stream(emme_pic* s);
+/* Multi-GPU (markers sharded over ranks).  emme_pic_create_shard takes ALL n_markers markers (so
+ * that the p_weight normalisation over all markers, include/solver_pic.h:229-235, is formed in
+ * the reference's order) and keeps the contiguous block shard_index of shard_count on the
+ * device.  With shard_count > 1 a stage stops after the deposit: the caller sums the density
+ * (emme_pic_density_ptr: 2*npoints doubles on the device) over the ranks between
+ * emme_pic_stage_begin and emme_pic_stage_finish, which applies the quasi-neutrality table
+ * (and records the field after stage 2).  emme_pic_step does all of this for one rank only. */
+int emme_pic_create_shard(const emme_pic_params* p, long n_markers, const double* eta,
+                          const double* v_para, const double* v_perp, const double* weight,
+                          int shard_index, int shard_count, int device, emme_pic** out);
+int emme_pic_stage_begin(emme_pic* s, double dt, int stage);
+int emme_pic_stage_finish(emme_pic* s, int stage);
+void* emme_pic_density_ptr(emme_pic* s);
+/* input.json -> PIC parameters (keys marker_per_cell, step_number, time_step: src/main.cpp:89-94) */
+int emme_input_pic_params(const emme_input* in, emme_pic_params* p, long* marker_per_cell,
+                          long* step_number, double* time_step);
+
 #ifdef __cplusplus
 }
 #endif

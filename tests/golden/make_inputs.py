@@ -52,6 +52,18 @@ def main():
         t = sub1(c1, r'"conf": "tokamak"', f'"conf": "{conf}"')
         (OUT / f"c1_{tag}_n64.json").write_text(sub1(t, r'"npoints": 1024', '"npoints": 64'))
 
+    # PIC method (row N4): the shipped file with the scan object collapsed, small meshes
+    pic = sub1(ex, r'"omega_d_coeff":\{[^}]*\}', '"omega_d_coeff": 1.0')
+    (OUT / "pic.json").write_text(pic)
+    p32 = sub1(sub1(pic, r'"npoints": 1024', '"npoints": 32'), r'"marker_per_cell":1024', '"marker_per_cell":32')
+    (OUT / "pic_n32.json").write_text(p32)
+    (OUT / "pic_n32_noswitch.json").write_text(
+        sub1(p32, r'"drift_center_transformation_switch":true', '"drift_center_transformation_switch":false'))
+    wb = sub1(sub1(pic, r'"npoints": 1024', '"npoints": 64'), r'"marker_per_cell":1024', '"marker_per_cell":24')
+    wb = sub1(wb, r'"water_bag_weight_vpara": 1.0', '"water_bag_weight_vpara": 0.5')
+    wb = sub1(wb, r'"water_bag_weight_vperp": 1.0', '"water_bag_weight_vperp": 1.5')
+    (OUT / "pic_n64_wb.json").write_text(wb)
+
     st = (REF / "input-stellarator-example.json").read_text()
     extra = ('    "method":"eigen",\n    "iteration_method":"TraceSecant",\n    "epsilon_r":0.0,\n'
              '    "omega_d_coeff":1.0,\n    "water_bag_weight_vpara":1.0,\n'

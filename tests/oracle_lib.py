@@ -142,3 +142,99 @@ def integrate(fn, tol, prec, maxdepth, order):
 
 def have_ref_driver():
     return REF_DRIVER.exists() and os.access(REF_DRIVER, os.X_OK)
+
+
+# ---- PIC method (row N4): oracle/emme_pic_oracle.c ------------------------------------------
+PIC_LIB = ROOT / "oracle" / "_ref" / "libemme_pic_oracle.so"
+PIC_DRIVER = ROOT / "oracle" / "_ref" / "pic_driver"
+
+
+class PicOracleParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("q", "R", "vt", "tau", "shat", "b_theta", "length", "eta_i", "omega_s_i", "omega_d_bar",
+                 "water_bag_weight_vpara", "water_bag_weight_vperp")] + [
+        ("npoints", C.c_int), ("drift_center_transformation_switch", C.c_int)]
+
+
+_pic_lib = None
+
+
+def pic_lib():
+    global _pic_lib
+    if _pic_lib is None:
+        src = ROOT / "oracle" / "emme_pic_oracle.c"
+        if not PIC_LIB.exists() or PIC_LIB.stat().st_mtime < src.stat().st_mtime:
+            subprocess.run(["make", "-C", str(ROOT / "oracle"), "port"], check=True, stdout=subprocess.DEVNULL)
+        L = C.CDLL(str(PIC_LIB))
+        dp = C.POINTER(C.c_double)
+        L.emme_pic_oracle_create.restype = C.c_void_p
+        L.emme_pic_oracle_create.argtypes = [C.POINTER(PicOracleParams), C.c_long, dp, dp, dp, dp]
+        L.emme_pic_oracle_destroy.argtypes = [C.c_void_p]
+        L.emme_pic_oracle_step.argtypes = [C.c_void_p, C.c_double]
+        L.emme_pic_oracle_field.argtypes = [C.c_void_p, dp]
+        L.emme_pic_oracle_markers.argtypes = [C.c_void_p, dp, dp]
+        L.emme_pic_oracle_extras.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.emme_pic_oracle_calculate_omega.argtypes = [dp, C.c_long, C.c_double, dp, dp]
+        L.emme_shim_cyl_bessel_j.restype = C.c_double
+        L.emme_shim_cyl_bessel_j.argtypes = [C.c_double, C.c_double]
+        _pic_lib = L
+    return _pic_lib
+
+
+class PicOracle:
+    """The plain-C restatement of PIC_State + Integrator (include/solver_pic.h)."""
+
+    def __init__(self, params, eta, v_para, v_perp, weight):
+        self.L = pic_lib()
+        self.p = PicOracleParams(**{k: params[k] for k, _ in PicOracleParams._fields_})
+        self.n = len(eta)
+        self.nf = self.p.npoints
+        eta, v_para, v_perp = (np.ascontiguousarray(a, dtype=np.float64) for a in (eta, v_para, v_perp))
+        weight = np.ascontiguousarray(weight, dtype=np.complex128)
+        self.h = self.L.emme_pic_oracle_create(C.byref(self.p), self.n, _dp(eta), _dp(v_para), _dp(v_perp),
+                                               _dp(weight.view(np.float64)))
+
+    def step(self, dt):
+        self.L.emme_pic_oracle_step(self.h, dt)
+
+    def field(self):
+        f = np.empty(self.nf, dtype=np.complex128)
+        self.L.emme_pic_oracle_field(self.h, _dp(f.view(np.float64)))
+        return f
+
+    def markers(self):
+        eta = np.empty(self.n)
+        w = np.empty(self.n, dtype=np.complex128)
+        self.L.emme_pic_oracle_markers(self.h, _dp(eta), _dp(w.view(np.float64)))
+        return eta, w
+
+    def extras(self):
+        a, b, c = (np.empty(self.n) for _ in range(3))
+        coef = np.empty(self.nf)
+        self.L.emme_pic_oracle_extras(self.h, _dp(a), _dp(b), _dp(c), _dp(coef))
+        return a, b, c, coef
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.emme_pic_oracle_destroy(self.h)
+            self.h = None
+
+
+def pic_calculate_omega(stats, dt):
+    stats = np.ascontiguousarray(stats, dtype=np.float64)
+    re, im = C.c_double(), C.c_double()
+    pic_lib().emme_pic_oracle_calculate_omega(_dp(stats), stats.shape[0], dt, C.byref(re), C.byref(im))
+    return complex(re.value, im.value)
+
+
+def pic_field_stats(fields):
+    """Per-step diagnostics of src/main.cpp:110-117 in the reference's accumulation order."""
+    out = np.empty((fields.shape[0], 3))
+    for k, f in enumerate(fields):
+        re = im = nrm = 0.0
+        for v in f:
+            re += v.real
+            im += v.imag
+            nrm += v.real * v.real + v.imag * v.imag
+        out[k] = (re / f.size, im / f.size, np.sqrt(nrm / f.size))
+    return out
