@@ -19,7 +19,7 @@ EXE = PKG / "bin" / "emme"
 
 CU_SOURCES = [PKG / "csrc" / n for n in ("assembly.cu", "dense.cu", "qr.cu", "pic.cu", "capi.cu")]
 HOST_SOURCES = [PKG / "host" / n for n in ("json.cpp", "parameters.cpp")]
-EXE_SOURCES = [PKG / "host" / n for n in ("eigen_solver.cpp", "main.cpp")]
+EXE_SOURCES = [PKG / "host" / n for n in ("eigen_solver.cpp", "pic_solver.cpp", "main.cpp")]
 HEADERS = (list((PKG / "csrc").glob("*.h")) + list((PKG / "csrc").glob("*.cuh")) +
            list((PKG / "host").glob("*.hpp")) + [ROOT / "include" / "emme_b200.h"])
 

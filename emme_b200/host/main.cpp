@@ -8,12 +8,14 @@
 // Scan objects {head, step, tail} follow the reference's generator and its continuation of omega
 // between scan points (src/main.cpp:139-172,262-325); a failing point is recorded as
 // {"eigenvalue": "NaN", "reason": ...} and the scan continues (src/main.cpp:300-318).
-// Only method "eigen" is implemented, with both iteration methods;
-// anything else raises the reference's "not supported" error text.
+// Methods "eigen" (both iteration methods) and "PIC" (row N4, src/main.cpp:82-137) are
+// implemented; anything else raises the reference's "not supported" error text.  The PIC marker
+// loading is seeded from std::random_device like the reference unless EMME_PIC_SEED is set.
 #include <array>
 #include <chrono>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <ctime>
 #include <fstream>
 #include <iomanip>
@@ -26,6 +28,7 @@
 #include "eigen_solver.hpp"
 #include "json.hpp"
 #include "parameters.hpp"
+#include "pic_solver.hpp"
 
 using emme::json::Value;
 using clk = std::chrono::steady_clock;
@@ -98,6 +101,47 @@ Value solve_once_eigen(const Value& input, std::complex<double>& omega_initial_g
     return single;
 }
 
+// solve_once_pic (src/main.cpp:82-137): the time loop runs on the device in one call; the
+// per-step diagnostics the reference prints inside the loop are produced from the recorded
+// field history afterwards, in the reference's format.
+Value solve_once_pic(const Value& input, std::complex<double>&, std::ofstream& eigen_matrix_file) {
+    timers.begin("Initial");
+    auto para = emme::Parameters::generate(input);
+    const std::size_t marker_per_cell = (std::size_t)input.at("marker_per_cell").number();
+    long long seed = -1;
+    if (const char* e = std::getenv("EMME_PIC_SEED")) seed = std::atoll(e);
+    emme::PIC_State state(*para, marker_per_cell, seed);
+    emme::Integrator integrator(state);
+    const std::size_t nt = (std::size_t)input.at("step_number").number();
+    const double dt = input.at("time_step");
+    timers.end("Initial");
+
+    timers.begin("Particle Pushing + Field Solve");
+    if (nt > 0) integrator.step(dt);          // Integrator::step once through the mirror ...
+    if (nt > 1) state.step(dt, (int)nt - 1);  // ... and the rest of the loop in one device call
+    timers.end("Particle Pushing + Field Solve");
+
+    timers.begin("Diagnostics");
+    const auto history = state.field_history(0, (long)nt);
+    const std::size_t nf = (std::size_t)para->npoints;
+    eigen_matrix_file.write(reinterpret_cast<const char*>(history.data()),
+                            sizeof(std::complex<double>) * history.size());
+    const auto stats = state.field_stats(0, (long)nt);
+    for (std::size_t idx = 0; idx < nt; ++idx)
+        std::cout << "        " << idx + 1 << '/' << nt << " phi[0]: " << history[idx * nf + nf / 2] << '\n';
+    timers.end("Diagnostics");
+
+    const auto eigen_value = emme::util::calculate_omega(stats, dt);
+    std::cout << "        Eigenvalue: " << eigen_value << '\n';
+    Value single = Value::object();
+    Value ev = Value::array(2);
+    ev[0] = Value(eigen_value.real());
+    ev[1] = Value(eigen_value.imag());
+    single["eigenvalue"] = ev;
+    single["eigenvector"] = Value::complex_array(state.current_field());
+    return single;
+}
+
 // get_scan_generator (src/main.cpp:139-172) as a stateful object
 struct ScanGenerator {
     double head, step, left_tail, right_tail, current, current_tail;
@@ -134,6 +178,7 @@ int main() {
     auto invoke_solver = [&](const Value& in, std::complex<double>& w, std::ofstream& f) {
         const std::string method = input_all.at("method").as_string();
         if (method == "eigen") return solve_once_eigen(in, w, f);
+        if (method == "PIC") return solve_once_pic(in, w, f);
         throw std::runtime_error("Method '" + method + "' is not supported, yet.\n");
     };
     timers.begin("All");

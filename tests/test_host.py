@@ -154,6 +154,14 @@ def test_host_program_fails_loudly_without_gpu(tmp_path, native_lib):
     assert '"scan_key": "omega_d_coeff"' in txt
 
 
-def test_host_program_rejects_pic(tmp_path, native_lib):
-    r = _run_emme(tmp_path, cases.input_path("c1_n32").read_text().replace('"method": "eigen"', '"method": "PIC"'))
-    assert r.returncode != 0 and "Method 'PIC' is not supported, yet." in r.stderr
+def test_host_program_rejects_unknown_method(tmp_path, native_lib):
+    r = _run_emme(tmp_path, cases.input_path("c1_n32").read_text().replace('"method": "eigen"', '"method": "fluid"'))
+    assert r.returncode != 0 and "Method 'fluid' is not supported, yet." in r.stderr
+
+
+def test_host_program_pic_fails_loudly_without_gpu(tmp_path, native_lib):
+    """`"method": "PIC"` (row N4) goes to the device path; without a device it aborts."""
+    if native_lib.emme_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = _run_emme(tmp_path, cases.input_path("pic_n32").read_text())
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)

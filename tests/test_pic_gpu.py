@@ -126,3 +126,31 @@ def test_full_size_properties(native_lib):
     d = np.abs(finals[0][0] - expect)
     d = np.minimum(d, 2 * L - d)
     assert d.max() <= 1e-12 * L
+
+
+def test_host_program_pic_end_to_end(tmp_path, native_lib, monkeypatch):
+    """The C++ `emme` program with the shipped method: input.json -> output.json + the per-step
+    field stream in eigenMatrics/eigenMatrix.bin (src/main.cpp:104-108), against the reference's
+    dump of the same seed for the steps the fixture holds and the Python mirror for the rest."""
+    import re
+    import subprocess
+    from emme_b200 import build
+    build.build_all()
+    g, p, mpc, dt = load_case("n32")
+    (tmp_path / "input.json").write_text((cases.GOLD / "inputs" / "pic_n32.json").read_text())
+    (tmp_path / "eigenMatrics").mkdir()
+    monkeypatch.setenv("EMME_PIC_SEED", str(int(g["seed"])))
+    r = subprocess.run([str(build.EXE)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    nt = 180
+    assert r.stdout.count(" phi[0]: ") == nt and f"        {nt}/{nt} phi[0]: (" in r.stdout
+    F = np.fromfile(tmp_path / "eigenMatrics" / "eigenMatrix.bin", dtype=np.complex128).reshape(nt, p.npoints)
+    for t in range(int(g["steps"])):
+        assert np.abs(F[t] - g["fields"][t]).max() <= FIELD_TOL * np.abs(g["fields"][t]).max()
+    res = pic.solve_once_pic(Input(cases.GOLD / "inputs" / "pic_n32.json"), seed=int(g["seed"]))
+    out = (tmp_path / "output.json").read_text()
+    m = re.search(r'"eigenvalue": \[\s*([-0-9.e]+),\s*([-0-9.e]+)', out)
+    assert abs(float(m.group(1)) - res["eigenvalue"][0]) < 1e-5 and abs(float(m.group(2)) - res["eigenvalue"][1]) < 1e-5
+    assert '"scan_key": "(None)"' in out and '"eigenvector"' in out
+    # run-to-run: deposits are summed in a varying order, so only to rounding
+    assert np.abs(F[-1] - res["eigenvector"]).max() <= 1e-9 * np.abs(F[-1]).max()
