@@ -22,7 +22,10 @@ two assemblies are counted, nothing is skipped).
             ranks, one NCCL all-reduce per assembly, reported in the extra key "row_sharded"
 
 Extra keys: roofline (kernel 1, FP64 pipe), roofline_dense (kernel 2), cpu_baseline (oracle/_ref on
-the box's host cores, bounded sample), c1 (converged-eigenvalue time of input-example.json), sweep.
+the box's host cores, bounded sample), c1 (converged-eigenvalue time of input-example.json), sweep,
+pic (row N4: input-example.json AS SHIPPED, method PIC -- BASELINE configs[0] -- marker-stages/s of
+the fused stage kernel against the HBM roofline, the whole run through solve_once_pic with host
+buffers, and the reference's PIC_State/Integrator on the host cores for a few steps).
 """
 import argparse
 import json
@@ -39,6 +42,12 @@ sys.path.insert(0, str(ROOT))
 
 C1_PATH = ROOT / "tests" / "golden" / "inputs" / "c1.json"
 REF_DRIVER = ROOT / "oracle" / "_ref" / "ref_driver"
+PIC_PATH = ROOT / "tests" / "golden" / "inputs" / "pic.json"
+PIC_DRIVER = ROOT / "oracle" / "_ref" / "pic_driver"
+# algorithmic HBM bytes of the PIC stage kernel per marker and Integrator::step (three stages):
+# per stage load eta 8 + w 16 + A 16 + B 16 + v_para 8 + v_perp 8 + p_weight 8 = 80 B and store
+# eta 8 + w 16 + A 16 + B 16 = 56 B; the stage-1 velocity is stored once (16 B) and loaded once (16 B)
+PIC_BYTES_PER_MARKER_STEP = 3 * (80 + 56) + 32
 FLOP_FIXED = 194 + 20 * 8      # fixed complex arithmetic + 8 transcendentals
 FLOP_TRIP = 14                 # per Miller recurrence trip
 
@@ -197,6 +206,66 @@ def timed_iterates(solver, inp, omega0, steps, tol, reseed_points, e2e=None):
             solver.seed(solver.eigen_value)              # continuation from the converged omega
             out["assemblies"] += 2
             out["reseeds"] += 1
+    return out
+
+
+def bench_pic(device, hbm_peak):
+    """Row N4: the PIC method of input-example.json as shipped (1024 cells x 1024 markers per cell,
+    180 steps of 0.25) and a 16x larger marker count, where the state no longer fits the L2."""
+    from emme_b200 import Input, pic
+    inp = Input(PIC_PATH)
+    p, mpc, nt, dt = pic.pic_params(inp)
+    out = {"workload": "input-example.json as shipped: method PIC, 1024 cells x 1024 markers per cell, "
+                       f"{nt} steps of {dt} (three Runge-Kutta stages each)", "dtype": "f64"}
+    try:
+        traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get("pic_stage_kernel", {})
+    except Exception:
+        traffic = {}
+    for key, m, steps in (("default", mpc, nt), ("markers_x16", 16 * mpc, 20)):
+        markers = pic.load_markers(p, m * p.npoints, seed=1)
+        s = pic.PIC_State.from_markers(p, *markers, device=device)
+        s.step(dt, 3)                               # warm-up, graph capture
+        ms = []
+        for _ in range(3):
+            s.step(dt, steps)
+            ms.append(s.timing()[0])
+        t = min(ms) * 1e-3
+        n = s.marker_num()
+        gbs = PIC_BYTES_PER_MARKER_STEP * n * steps / t / 1e9
+        tr = traffic.get(str(n))
+        out[key] = {"markers": n, "cells": p.npoints, "steps": steps, "ms_per_step": 1e3 * t / steps,
+                    "us_per_stage": 1e6 * t / steps / 3, "marker_stages_per_s": 3.0 * n * steps / t,
+                    "gpu_launches_per_step": 6,
+                    "roofline": {"kernel": "pic_stage_kernel (+ pic_field_kernel)", "bound": "hbm", "achieved": gbs,
+                                 "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "algorithmic_bytes_per_marker_step": PIC_BYTES_PER_MARKER_STEP,
+                                 "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
+                                 "traffic_note": tr["note"] if tr else None}}
+        s.close()
+    # the whole default run through the public API with host buffers: marker loading on the host,
+    # upload, 180 steps, download of the field history, diagnostics and eigenvalue
+    pic.solve_once_pic(inp, seed=1, device=device)   # warm
+    t0 = time.perf_counter()
+    res = pic.solve_once_pic(inp, seed=1, device=device)
+    t1 = time.perf_counter()
+    n = mpc * p.npoints
+    out["e2e"] = {"seconds": t1 - t0, "marker_stages_per_s": 3.0 * n * nt / (t1 - t0),
+                  "h2d_bytes": 48 * n, "d2h_bytes": 16 * p.npoints * nt,
+                  "eigenvalue": res["eigenvalue"],
+                  "note": "solve_once_pic: std::mt19937 marker loading and v_perp sort on one host core, upload, "
+                          "all steps, field history download, util::calculate_omega; the eigen method gives "
+                          "omega = (-0.8235, 0.2585) for the same physics (the PIC frequency carries no sign)"}
+    if PIC_DRIVER.exists():
+        r = subprocess.run([str(PIC_DRIVER), "time", str(PIC_PATH), "1", "4"], capture_output=True, text=True,
+                           timeout=600)
+        if r.returncode == 0:
+            c = json.loads(r.stdout.strip().splitlines()[-1])
+            out["cpu_baseline"] = {"value": c["marker_stages_per_s"], "unit": "marker-stages/s",
+                                   "cores": c["threads"], "kind": "reference",
+                                   "sample": f"reference PIC_State + Integrator (oracle/_ref/pic_driver, unmodified "
+                                             f"include/solver_pic.h) on {c['threads']} host threads: {c['steps']} of "
+                                             f"{nt} steps of the same {c['markers']} markers in {c['seconds']:.2f} s",
+                                   "est_s_per_run": c["seconds"] / c["steps"] * nt}
     return out
 
 
@@ -362,6 +431,9 @@ def bench_b200(args, rank, local_rank, world):
                           "assemble_frac_of_fp64_peak": fl / (ss_["assemble_ms"] * 1e-3) / 1e12 / peak_tf.value})
             sv.close()
         extra["sweep"] = sweep
+
+    if rank == 0 and world == 1 and not args.quick:
+        extra["pic"] = bench_pic(local_rank, hbm_peak)
 
     row_sharded = None
     if world > 1 and args.mode_rows:

@@ -15,16 +15,19 @@
 //            order, so eta is bit-identical to the reference's
 //   deposit  at the new eta: J0, J1 from ONE Miller backward recurrence (`bessel_j01`), the
 //            pull-back phase exp(-i omega_d_integral omega_dv) from one sincos, density
-//            j0 w dc_pb into per-CTA shared-memory cells (shared atomics), then one
-//            red.global.add.f64 per touched cell and CTA
+//            j0 w dc_pb into per-CTA shared-memory cells (shared atomics); every CTA then
+//            stores its cells as one partial density (plain coalesced stores)
 //   next     the marker's velocity coefficients A, B for the NEXT stage are formed now, while
 //            j0, dj0, dc_pb, omega_d(eta) are in registers: what crosses the field solve per
 //            marker is (eta, w, A, B) = 56 bytes instead of the reference's j0/dc_pb extras
 //            plus a second Bessel evaluation
-//   field    the last CTA to finish (ticket) turns the summed density into the new field
-//            (quasi-neutrality table, :349-351), clears the accumulators and, after stage 2,
-//            appends the field to the on-device history that the diagnostics read.
-// Three launches per Integrator::step, captured once per dt into a CUDA graph and replayed.
+//   field    `pic_field_kernel` sums the per-CTA partials in a fixed order and turns the density
+//            into the new field (quasi-neutrality table, :349-351); after stage 2 it appends the
+//            field to the on-device history that the diagnostics read.
+// Six launches per Integrator::step, captured once per dt into a CUDA graph and replayed.
+// (The first version flushed the cells with red.global.add.f64 and let the last CTA form the
+// field: 592 CTAs adding into the same 128 cache lines serialised at ~8 cycles per atomic and
+// line, 20 of 49 us per stage at 1M markers; see DESIGN.md.)
 //
 // Differences to the reference that are visible in the numbers: deposits are summed in a
 // different (and run-to-run varying) order, Bessel J comes from the Miller recurrence (abs. error
@@ -32,9 +35,12 @@
 // factored form; fields agree with the reference to ~1e-13 relative (tests/test_pic_gpu.py).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
+#include <numeric>
 #include <random>
 #include <string>
 #include <vector>
@@ -60,11 +66,12 @@ struct PicDev {
     const double *vpar, *vperp, *pw;
     d2 *w, *A, *B, *k1;
     double* c;  // omega_d(eta) * omega_dv, only without the pull-back transformation
-    d2 *field, *dens;
+    d2 *field, *dens;   // dens: summed density (the buffer a multi-GPU exchange reduces)
+    d2* part;           // per-CTA partial densities [nparts][nf] (shared-memory cells only)
+    int nparts;
     const double* coef;
     d2* hist;
-    unsigned* ticket;
-    unsigned long long* step;
+    unsigned long long* step;   // Integrator::step calls started
 };
 
 __device__ __forceinline__ void deposit(const PicDev& d, d2* cells, double eta, d2 den) {
@@ -79,26 +86,47 @@ __device__ __forceinline__ void deposit(const PicDev& d, d2* cells, double eta, 
     atomicAdd(&cells[i1].y, den.y * wt);
 }
 
-// field = density * quasi-neutrality table (include/solver_pic.h:349-351); clears the density.
-__device__ __forceinline__ void finish_field(const PicDev& d, bool record) {
-    const unsigned long long slot = *d.step;
-    for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
-        const double2 raw = __ldcg(reinterpret_cast<const double2*>(&d.dens[i]));
-        const d2 v = mk2(raw.x, raw.y);
-        const double cf = d.coef[i];
-        const d2 f = mk2(v.x * cf, v.y * cf);
-        d.field[i] = f;
-        d.dens[i] = mk2(0.0, 0.0);
-        if (record) d.hist[slot * (unsigned long long)d.nf + i] = f;
+// Density -> field (include/solver_pic.h:339-351).  blockDim = (32 cells, 32 chunks): chunk c sums
+// the partials c, c+32, ... of its cell (all loads of a thread independent: one L2 round trip),
+// then the chunks are added in index order, so the result is deterministic for given partials.
+// mode 0: field = coef * sum(partials); mode 1 (multi-GPU, before the exchange):
+// dens = sum(partials); mode 2 (after the exchange): field = coef * dens.  Without shared-memory
+// cells the stage kernel has already accumulated into dens, which is cleared once it is consumed.
+#define PIC_FIELD_CHUNKS 32
+__global__ void __launch_bounds__(32 * PIC_FIELD_CHUNKS) pic_field_kernel(PicDev d, int mode, int record) {
+    __shared__ d2 red[PIC_FIELD_CHUNKS][32];
+    const int cell = blockIdx.x * 32 + threadIdx.x, ch = threadIdx.y;
+    d2 acc = mk2(0.0, 0.0);
+    const bool summed = (mode == 2) || !d.use_smem;
+    if (cell < d.nf) {
+        if (summed) {
+            if (ch == 0) acc = d.dens[cell];
+        } else {
+#pragma unroll 5
+            for (int g = ch; g < d.nparts; g += PIC_FIELD_CHUNKS) {
+                const d2 v = d.part[(size_t)g * d.nf + cell];
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+        }
     }
+    red[ch][threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        *d.ticket = 0;
-        if (record) *d.step = slot + 1;
+    if (ch != 0 || cell >= d.nf) return;
+    for (int c = 1; c < PIC_FIELD_CHUNKS; ++c) {
+        acc.x += red[c][threadIdx.x].x;
+        acc.y += red[c][threadIdx.x].y;
     }
+    if (mode == 1) {
+        d.dens[cell] = acc;
+        return;
+    }
+    const double cf = d.coef[cell];
+    const d2 f = mk2(acc.x * cf, acc.y * cf);
+    d.field[cell] = f;
+    if (summed) d.dens[cell] = mk2(0.0, 0.0);
+    if (record) d.hist[(*d.step - 1) * (unsigned long long)d.nf + cell] = f;
 }
-
-__global__ void pic_field_kernel(PicDev d, int record) { finish_field(d, record != 0); }
 
 // First deposit-independent state: A = B = 0 (the reference's marker extras start with
 // j0 = dc_pb = 0, include/solver_pic.h:207-227, and the field with 0), c from the loaded eta.
@@ -114,15 +142,22 @@ __global__ void pic_init_kernel(PicDev d) {
     }
 }
 
+// register budget of the stage kernel: (1024, 1) allows 64 registers and any block size;
+// tuning builds pass -DPIC_LB_THREADS=256 -DPIC_LB_BLOCKS=5|6 (block size is then fixed at 256)
+#ifndef PIC_LB_THREADS
+#define PIC_LB_THREADS 1024
+#define PIC_LB_BLOCKS 1
+#endif
+
 // One Runge-Kutta stage for every marker.  h = coef[stage][stage+1] * dt; the stage's velocity
 // combination is v = k0 (stage 0), k1 (stage 1), c1 k1 + c2 k2 (stage 2).
 template <bool SWITCH, bool SMEM>
-__global__ void __launch_bounds__(256) pic_stage_kernel(PicDev d, int stage, double h, double c1,
-                                                        double c2, int finish) {
+__global__ void __launch_bounds__(PIC_LB_THREADS, PIC_LB_BLOCKS) pic_stage_kernel(PicDev d, int stage, double h, double c1,
+                                                        double c2) {
     extern __shared__ d2 smem[];
     d2* s_field = smem;
     d2* s_dens = smem + d.nf;
-    __shared__ bool s_last;
+    if (stage == 0 && blockIdx.x == 0 && threadIdx.x == 0) *d.step += 1;
     if (SMEM) {
         for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
             s_field[i] = d.field[i];
@@ -169,24 +204,8 @@ __global__ void __launch_bounds__(256) pic_stage_kernel(PicDev d, int stage, dou
     }
     if (SMEM) {
         __syncthreads();
-        // rotate the start cell by CTA so that concurrent CTAs hit different L2 lines
-        const int rot = (int)(((long)blockIdx.x * 97) % nf);
-        for (int j = threadIdx.x; j < nf; j += blockDim.x) {
-            int i = j + rot;
-            if (i >= nf) i -= nf;
-            const d2 v = s_dens[i];
-            if (v.x != 0.0) atomicAdd(&d.dens[i].x, v.x);
-            if (v.y != 0.0) atomicAdd(&d.dens[i].y, v.y);
-        }
-    }
-    if (!finish) return;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(d.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        finish_field(d, stage == 2);
+        d2* mine = d.part + (size_t)blockIdx.x * nf;
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) mine[i] = s_dens[i];
     }
 }
 
@@ -202,6 +221,8 @@ struct emme_pic {
     long n = 0, n_total = 0, first = 0;
     PicDev d{};
     std::vector<double> h_pw, h_vpar, h_vperp, h_coef;  // host copies for emme_pic_extras
+    std::vector<long> perm;  // device slot j holds marker perm[j] of this shard (sorted by v_perp)
+    int block = 256;
     void* d_vpar = nullptr;
     void* d_vperp = nullptr;
     void* d_pw = nullptr;
@@ -255,18 +276,24 @@ int ensure_history(emme_pic* s, long steps_total) {
     return 0;
 }
 
-cudaError_t launch_stage(emme_pic* s, double dt, int stage, int finish) {
+cudaError_t launch_stage(emme_pic* s, double dt, int stage) {
     const double h = RK_COEF[stage][stage + 1] * dt;
     const double c1 = RK_COEF[2][1], c2 = RK_COEF[2][2];
     const bool sw = s->p.drift_center_transformation_switch != 0;
-    dim3 grid(s->grid), block(256);
+    dim3 grid(s->grid), block(s->block);
     if (s->d.use_smem) {
-        if (sw) pic_stage_kernel<true, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2, finish);
-        else pic_stage_kernel<false, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2, finish);
+        if (sw) pic_stage_kernel<true, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2);
+        else pic_stage_kernel<false, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2);
     } else {
-        if (sw) pic_stage_kernel<true, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2, finish);
-        else pic_stage_kernel<false, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2, finish);
+        if (sw) pic_stage_kernel<true, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2);
+        else pic_stage_kernel<false, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2);
     }
+    s->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_field(emme_pic* s, int mode, int record) {
+    pic_field_kernel<<<(s->d.nf + 31) / 32, dim3(32, PIC_FIELD_CHUNKS), 0, s->stream>>>(s->d, mode, record);
     s->launches++;
     return cudaGetLastError();
 }
@@ -382,43 +409,64 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     CU(dev_alloc(&d.field, nf));
     CU(dev_alloc(&d.dens, nf));
     CU(dev_alloc(&dcoef, nf));
-    CU(dev_alloc(&d.ticket, 1));
     CU(dev_alloc(&d.step, 1));
     d.vpar = dvpar; d.vperp = dvperp; d.pw = dpw; d.coef = dcoef;
     s->d_vpar = dvpar; s->d_vperp = dvperp; s->d_pw = dpw; s->d_coef = dcoef;
-    CU(cudaMemcpyAsync(d.eta, eta + f0, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(dvpar, v_para + f0, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(dvperp, v_perp + f0, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(dpw, s->h_pw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(d.w, weight + 2 * f0, sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
+    // Device order: markers sorted by v_perp.  The Miller recurrence of bessel_j01 runs
+    // ~ x + 12.6 x^(1/3) trips with x = (v_perp/vt) sb(eta); lanes of a warp that share v_perp
+    // differ only through sb(eta), which halves the spread of trip counts inside a warp.  The
+    // order of markers is otherwise free (deposits commute); emme_pic_markers undoes it.
+    s->perm.resize(n);
+    std::iota(s->perm.begin(), s->perm.end(), 0L);
+    if (!std::getenv("EMME_PIC_NOSORT"))
+        std::stable_sort(s->perm.begin(), s->perm.end(),
+                         [&](long a, long b) { return v_perp[f0 + a] < v_perp[f0 + b]; });
+    {
+        std::vector<double> t_eta(n), t_vpar(n), t_vperp(n), t_pw(n), t_w(2 * (size_t)n);
+        for (long j = 0; j < n; ++j) {
+            const long i = f0 + s->perm[j];
+            t_eta[j] = eta[i];
+            t_vpar[j] = v_para[i];
+            t_vperp[j] = v_perp[i];
+            t_pw[j] = s->h_pw[s->perm[j]];
+            t_w[2 * j] = weight[2 * i];
+            t_w[2 * j + 1] = weight[2 * i + 1];
+        }
+        CU(cudaMemcpyAsync(d.eta, t_eta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dvpar, t_vpar.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dvperp, t_vperp.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dpw, t_pw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(d.w, t_w.data(), sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));   // the staging vectors go out of scope
+    }
     CU(cudaMemcpyAsync(dcoef, s->h_coef.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemsetAsync(d.field, 0, sizeof(d2) * nf, s->stream));
     CU(cudaMemsetAsync(d.dens, 0, sizeof(d2) * nf, s->stream));
-    CU(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), s->stream));
     CU(cudaMemsetAsync(d.step, 0, sizeof(unsigned long long), s->stream));
 
     // launch geometry: field + density cells in shared memory when they fit
     s->smem = sizeof(d2) * 2 * (size_t)nf;
     d.use_smem = s->smem <= 200 * 1024;
     const bool sw = p->drift_center_transformation_switch != 0;
+    // One 1024-thread CTA per SM once there are enough markers to fill them: the per-CTA costs
+    // (field copy, cell clearing, partial store, one more partial for pic_field_kernel to sum)
+    // are paid 148 instead of 592 times, and meshes whose cells take > 56 KB keep 32 warps per SM
+    s->block = (PIC_LB_THREADS >= 1024 && (n >= (long)s->sms * 1024 || s->smem > 56 * 1024)) ? 1024 : 256;
+    if (const char* e = std::getenv("EMME_PIC_BLOCK")) s->block = std::atoi(e);
     int per_sm = 1;
-    if (d.use_smem) {
-        if (sw) {
-            CU(cudaFuncSetAttribute(pic_stage_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<true, true>, 256, s->smem));
-        } else {
-            CU(cudaFuncSetAttribute(pic_stage_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<false, true>, 256, s->smem));
-        }
-    } else {
-        s->smem = 0;
-        if (sw) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<true, false>, 256, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pic_stage_kernel<false, false>, 256, 0));
+    {
+        const void* fn = d.use_smem ? (sw ? (const void*)pic_stage_kernel<true, true> : (const void*)pic_stage_kernel<false, true>)
+                                    : (sw ? (const void*)pic_stage_kernel<true, false> : (const void*)pic_stage_kernel<false, false>);
+        if (d.use_smem) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+        else s->smem = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->block, s->smem));
     }
     if (per_sm < 1) per_sm = 1;
-    const long want = (n + 255) / 256;
+    const long want = (n + s->block - 1) / s->block;
     const long cap = (long)s->sms * per_sm;
     s->grid = (int)(want < cap ? want : cap);
+    d.nparts = d.use_smem ? s->grid : 0;
+    CU(dev_alloc(&d.part, (size_t)d.nparts * nf));
     if (const char* e = std::getenv("EMME_PIC_GRAPH")) s->use_graph = std::atoi(e);
 
     const int ig = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
@@ -445,7 +493,7 @@ int emme_pic_destroy(emme_pic* s) {
     cudaFree(d.eta); cudaFree(s->d_vpar); cudaFree(s->d_vperp); cudaFree(s->d_pw);
     cudaFree(d.w); cudaFree(d.A); cudaFree(d.B); cudaFree(d.k1); cudaFree(d.c);
     cudaFree(d.field); cudaFree(d.dens); cudaFree(s->d_coef); cudaFree(d.hist);
-    cudaFree(d.ticket); cudaFree(d.step);
+    cudaFree(d.part); cudaFree(d.step);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -466,7 +514,10 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
         CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         const unsigned long long before = s->launches;
         cudaError_t e = cudaSuccess;
-        for (int st = 0; st < 3 && e == cudaSuccess; ++st) e = launch_stage(s, dt, st, 1);
+        for (int st = 0; st < 3 && e == cudaSuccess; ++st) {
+            e = launch_stage(s, dt, st);
+            if (e == cudaSuccess) e = launch_field(s, 0, st == 2);
+        }
         s->launches = before;
         cudaError_t e2 = cudaStreamEndCapture(s->stream, &g);
         if (e != cudaSuccess) return capi_fail(EMME_E_CUDA, std::string("stage launch: ") + cudaGetErrorString(e));
@@ -479,9 +530,12 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
     for (int k = 0; k < nsteps; ++k) {
         if (s->use_graph) {
             CU(cudaGraphLaunch(s->graph, s->stream));
-            s->launches += 3;
+            s->launches += 6;
         } else {
-            for (int st = 0; st < 3; ++st) CU(launch_stage(s, dt, st, 1));
+            for (int st = 0; st < 3; ++st) {
+                CU(launch_stage(s, dt, st));
+                CU(launch_field(s, 0, st == 2));
+            }
         }
     }
     CU(cudaEventRecord(s->ev1, s->stream));
@@ -499,7 +553,8 @@ int emme_pic_stage_begin(emme_pic* s, double dt, int stage) {
     CU(cudaSetDevice(s->device));
     if (stage == 0)
         if (int rc = ensure_history(s, s->steps_done + 1)) return rc;
-    CU(launch_stage(s, dt, stage, 0));
+    CU(launch_stage(s, dt, stage));
+    if (s->d.use_smem) CU(launch_field(s, 1, 0));   // dens = sum of this rank's partials
     return 0;
 }
 
@@ -507,9 +562,7 @@ int emme_pic_stage_finish(emme_pic* s, int stage) {
     if (!s) return capi_fail(-1, "null handle");
     if (stage < 0 || stage > 2) return capi_fail(-2, "stage must be 0, 1 or 2");
     CU(cudaSetDevice(s->device));
-    pic_field_kernel<<<1, 1024, 0, s->stream>>>(s->d, stage == 2);
-    s->launches++;
-    CU(cudaGetLastError());
+    CU(launch_field(s, 2, stage == 2));
     if (stage == 2) s->steps_done++;
     return 0;
 }
@@ -543,9 +596,18 @@ int emme_pic_field_history(emme_pic* s, long first, long count, void* host_out) 
 int emme_pic_markers(emme_pic* s, double* eta, double* weight) {
     if (!s) return capi_fail(-1, "null handle");
     CU(cudaSetDevice(s->device));
-    if (eta) CU(cudaMemcpyAsync(eta, s->d.eta, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
-    if (weight) CU(cudaMemcpyAsync(weight, s->d.w, sizeof(d2) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    std::vector<double> t_eta(eta ? s->n : 0), t_w(weight ? 2 * (size_t)s->n : 0);
+    if (eta) CU(cudaMemcpyAsync(t_eta.data(), s->d.eta, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (weight) CU(cudaMemcpyAsync(t_w.data(), s->d.w, sizeof(d2) * s->n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    for (long j = 0; j < s->n; ++j) {   // back to the caller's marker order
+        const long i = s->perm[j];
+        if (eta) eta[i] = t_eta[j];
+        if (weight) {
+            weight[2 * i] = t_w[2 * j];
+            weight[2 * i + 1] = t_w[2 * j + 1];
+        }
+    }
     return 0;
 }
 

@@ -41,10 +41,16 @@ PIC_HD d2 cmul2(d2 a, d2 b) { return mk2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y
 #define PIC_ADD(a, b) __dadd_rn((a), (b))
 #define PIC_MUL(a, b) __dmul_rn((a), (b))
 #define PIC_DIV(a, b) __ddiv_rn((a), (b))
+#define PIC_RCP(a) __drcp_rn(a)
+#define PIC_RSQRT(a) rsqrt(a)
+#define PIC_CBRTF(a) __powf((a), 0.33333334f)   /* only sizes the recurrence */
 #else
 #define PIC_ADD(a, b) ((a) + (b))   /* host builds use -ffp-contract=off */
 #define PIC_MUL(a, b) ((a) * (b))
 #define PIC_DIV(a, b) ((a) / (b))
+#define PIC_RCP(a) (1.0 / (a))
+#define PIC_RSQRT(a) (1.0 / sqrt(a))
+#define PIC_CBRTF(a) cbrtf(a)
 #endif
 
 // run constants of a PIC state
@@ -64,12 +70,14 @@ PIC_HD void bessel_j01(double x, double& j0, double& j1) {
         return;
     }
     const float xf = (float)x;
-    const int M = 2 * (int)ceilf(0.5f * (xf + 12.6f * cbrtf(xf) + 5.0f));
-    const double t = 2.0 / x;
+    const int M = 2 * (int)ceilf(0.5f * (xf + 12.6f * PIC_CBRTF(xf) + 5.2f));
+    const double t = 2.0 * PIC_RCP(x);
     double jp = 0.0, jk = 1.0, s = 0.0, kd = (double)M;
+#pragma unroll 2
     for (int k = M; k > 2; k -= 2) {
-        const double jm1 = fma(kd * t, jk, -jp);
-        const double jm2 = fma((kd - 1.0) * t, jm1, -jk);
+        const double a = kd * t;          // 2k/x
+        const double jm1 = fma(a, jk, -jp);
+        const double jm2 = fma(a - t, jm1, -jk);
         s += jm2;
         jp = jm1;
         jk = jm2;
@@ -77,13 +85,15 @@ PIC_HD void bessel_j01(double x, double& j0, double& j1) {
     }
     const double j1u = fma(2.0 * t, jk, -jp);
     const double j0u = fma(t, j1u, -jk);
-    const double inv = 1.0 / fma(2.0, s, j0u);
+    const double inv = PIC_RCP(fma(2.0, s, j0u));
     j0 = j0u * inv;
     j1 = j1u * inv;
 }
 
-// locate (include/solver_pic.h:245-249) with the reference's division; idx == nf (eta == +L
-// after rounding) wraps to cell 0.
+// locate (include/solver_pic.h:245-249) with the reference's division, so that the cell index
+// and the linear weight are the reference's bit for bit (a reciprocal multiply was measured:
+// it moves the weight by ulp(u) ~ 1e-12 on an 8192-cell mesh, visible against the oracle, and
+// the kernel is HBM-bound anyway); idx == nf (eta == +L after rounding) wraps to cell 0.
 PIC_HD void pic_locate(const PicConst& d, double eta, int& idx, double& wt) {
     const double u = PIC_DIV(PIC_ADD(eta, d.L), d.cw);
     const long long i = (long long)u;
@@ -115,8 +125,12 @@ PIC_HD d2 pic_velocity(const PicConst& d, const d2* fld, double eta, d2 A, d2 B)
 // eta <- bound(eta + v_para h/(qR)) in the reference's operation order
 // (include/solver_pic.h:143,401-404)
 PIC_HD double pic_push(const PicConst& d, double eta, double vpar, double h) {
-    double e = PIC_ADD(eta, PIC_DIV(PIC_MUL(vpar, h), d.qR));
-    e = fmod(PIC_ADD(e, d.L), 2.0 * d.L);
+    double e = PIC_ADD(PIC_ADD(eta, PIC_DIV(PIC_MUL(vpar, h), d.qR)), d.L);
+    // fmod(e, 2L): for -2L < e < 4L it is e or e - 2L, both exact; anything else (a marker
+    // crossing more than the whole domain in one stage) takes the library call
+    const double twoL = 2.0 * d.L;
+    if (e >= twoL) e = (e < 2.0 * twoL) ? PIC_ADD(e, -twoL) : fmod(e, twoL);
+    else if (e <= -twoL) e = fmod(e, twoL);
     return e < 0 ? PIC_ADD(e, d.L) : PIC_ADD(e, -d.L);
 }
 
@@ -129,10 +143,11 @@ PIC_HD void pic_marker_at(const PicConst& d, double eta, double vpar, double vpe
     sincos(eta, &se, &ce);
     const double xperp = vperp * d.inv_vt;
     const double sh_eta = d.shat * eta;
-    const double sb = sqrt(d.b_theta * fma(sh_eta, sh_eta, 1.0));
+    const double sb2 = d.b_theta * fma(sh_eta, sh_eta, 1.0);
+    const double rsb = PIC_RSQRT(sb2);   // 1/sb
     double j0, j1;
-    bessel_j01(xperp * sb, j0, j1);
-    const double dj0 = -d.b_theta * d.shat * d.shat * xperp * eta * j1 / sb;
+    bessel_j01(xperp * (sb2 * rsb), j0, j1);
+    const double dj0 = -d.b_theta * d.shat * d.shat * xperp * eta * j1 * rsb;
     const double v2 = vpar * vpar, p2 = vperp * vperp;
     const double odv = (v2 + 0.5 * p2) * d.inv_2vt2;
     const double ost = d.omega_s_i * (1.0 + d.eta_i * ((v2 + p2) * d.inv_2vt2 - 1.5));
@@ -142,7 +157,7 @@ PIC_HD void pic_marker_at(const PicConst& d, double eta, double vpar, double vpe
     const d2 a = mk2(-cpar * dj0, (ost - od * odv) * j0);
     const double b = -cpar * j0;
     if (SWITCH) {
-        const double odi = (d.qR / vpar) * d.omega_d_bar * (se * (1.0 + d.shat) - sh_eta * ce);
+        const double odi = (d.qR * PIC_RCP(vpar)) * d.omega_d_bar * (se * (1.0 + d.shat) - sh_eta * ce);
         double sp, cp;
         sincos(-odi * odv, &sp, &cp);
         den = cmul2(mk2(j0 * w.x, j0 * w.y), mk2(cp, sp));
