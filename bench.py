@@ -221,7 +221,7 @@ def bench_pic(device, hbm_peak):
         traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get("pic_stage_kernel", {})
     except Exception:
         traffic = {}
-    for key, m, steps in (("default", mpc, nt), ("markers_x16", 16 * mpc, 20)):
+    for key, m, steps in (("default", mpc, nt), ("markers_x4", 4 * mpc, 40), ("markers_x16", 16 * mpc, 20)):
         markers = pic.load_markers(p, m * p.npoints, seed=1)
         s = pic.PIC_State.from_markers(p, *markers, device=device)
         s.step(dt, 3)                               # warm-up, graph capture
@@ -460,6 +460,36 @@ def bench_b200(args, rank, local_rank, world):
                                     "NCCL all-reduce(sum) of disjoint shares, 16*dim^2 bytes per assembly")}
         ss.close()
 
+    pic_sharded = None
+    if world > 1 and not args.quick:
+        # row N4 across GPUs (weak scaling): 4 x 1024 x 1024 markers per GPU in contiguous blocks,
+        # one NCCL all-reduce of the density (2 * npoints doubles) per Runge-Kutta stage
+        from emme_b200 import pic
+        pinp = Input(PIC_PATH)
+        pp, mpc, _, pdt = pic.pic_params(pinp)
+        per_gpu = 4 * mpc * pp.npoints
+        markers = pic.load_markers(pp, per_gpu * world, seed=1)
+        sp = parallel.ShardedPIC(pp, markers, device=local_rank)
+        del markers
+        sp.step(pdt, 3)
+        sp.synchronize()
+        psteps = 40
+        barrier()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pext = torch.cuda.ExternalStream(sp.state.stream(), device=local_rank)
+        pe0.record(pext)
+        sp.step(pdt, psteps)
+        pe1.record(pext)
+        barrier()
+        pms = max_over_ranks(pe0.elapsed_time(pe1))
+        f_last = sp.current_field()
+        pic_sharded = {"scaling": "weak", "markers_per_gpu": per_gpu, "markers": per_gpu * world,
+                       "cells": pp.npoints, "steps": psteps, "ms_per_step": pms / psteps,
+                       "marker_stages_per_s": 3.0 * per_gpu * world * psteps / (pms * 1e-3), "unit": "marker-stages/s",
+                       "exchange": "one NCCL all-reduce (sum) of 2*npoints doubles per stage on the handle's stream",
+                       "field_rms": float(np.sqrt(np.mean(np.abs(f_last) ** 2)))}
+        sp.close()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and REF_DRIVER.exists() and not args.quick:
         tmp = Path(os.environ.get("TMPDIR", "/tmp")) / f"emme_bench_c1_n{npoints}.json"
@@ -524,6 +554,8 @@ def bench_b200(args, rank, local_rank, world):
             line["cpu_baseline"] = cpu_baseline
         if row_sharded:
             line["row_sharded"] = row_sharded
+        if pic_sharded:
+            line["pic_sharded"] = pic_sharded
         line.update(extra)
         print(json.dumps(line))
     solver.close()

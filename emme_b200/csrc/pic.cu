@@ -417,10 +417,24 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     // differ only through sb(eta), which halves the spread of trip counts inside a warp.  The
     // order of markers is otherwise free (deposits commute); emme_pic_markers undoes it.
     s->perm.resize(n);
-    std::iota(s->perm.begin(), s->perm.end(), 0L);
-    if (!std::getenv("EMME_PIC_NOSORT"))
-        std::stable_sort(s->perm.begin(), s->perm.end(),
-                         [&](long a, long b) { return v_perp[f0 + a] < v_perp[f0 + b]; });
+    if (std::getenv("EMME_PIC_NOSORT")) {
+        std::iota(s->perm.begin(), s->perm.end(), 0L);
+    } else {
+        // counting sort on 4096 buckets of v_perp (stable, O(n)): warps only need similar values
+        const int NB = 4096;
+        double vmax = 0;
+        for (long i = 0; i < n; ++i) vmax = std::max(vmax, v_perp[f0 + i]);
+        const double scale = vmax > 0 ? (NB - 1) / vmax : 0.0;
+        std::vector<long> start(NB + 1, 0);
+        std::vector<unsigned short> bucket(n);
+        for (long i = 0; i < n; ++i) {
+            const double b = v_perp[f0 + i] * scale;
+            bucket[i] = (unsigned short)(b > 0 ? (b < NB - 1 ? (int)b : NB - 1) : 0);
+            ++start[bucket[i] + 1];
+        }
+        for (int b = 0; b < NB; ++b) start[b + 1] += start[b];
+        for (long i = 0; i < n; ++i) s->perm[start[bucket[i]]++] = i;
+    }
     {
         std::vector<double> t_eta(n), t_vpar(n), t_vperp(n), t_pw(n), t_w(2 * (size_t)n);
         for (long j = 0; j < n; ++j) {

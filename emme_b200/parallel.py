@@ -15,6 +15,10 @@ Two ways the path shards:
   all-reduce (sum) completes the matrix; the shares are disjoint, so either way the result is
   bit-identical to a single-GPU assembly.  The dense step is replicated on every rank (identical
   inputs give identical delta, no broadcast needed).  `ShardedEigenSolver`.
+* PIC method (row N4): the markers are dealt to ranks in contiguous blocks (`marker_shard`); every
+  Runge-Kutta stage deposits the rank's markers and ends with ONE all-reduce (sum) of the density,
+  2 * npoints doubles (16 KB at 1024 cells) -- the path's only real exchange step -- after which
+  every rank applies the quasi-neutrality table and holds the same field.  `ShardedPIC`.
 """
 import ctypes as C
 
@@ -100,6 +104,77 @@ def solve_scan_parallel(base_text, key, values, omega0, device=0, group=None):
     if solver is not None:
         solver.close()
     return gather_results(local)
+
+
+def marker_shard(n_markers, rank, world):
+    """(first, count) of the contiguous block of markers rank `rank` keeps (the same split as
+    emme_pic_create_shard in emme_b200/csrc/pic.cu)."""
+    per, rem = divmod(n_markers, world)
+    return rank * per + min(rank, rem), per + (1 if rank < rem else 0)
+
+
+class _DevVector:
+    """Zero-copy torch view of `count` doubles of handle-owned device memory."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {
+            "shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class ShardedPIC:
+    """PIC_State + Integrator with the markers split over the ranks of a process group.
+
+    Every rank passes ALL markers (the p_weight normalisation runs over all of them, in the
+    reference's order) and keeps its block.  step() runs, per stage, the rank's stage kernel, one
+    NCCL all-reduce of the density on the handle's stream, and the field kernel; no host
+    synchronisation inside a step.  Every rank ends with the same field history."""
+
+    def __init__(self, params, markers, device=0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .pic import PIC_State
+        self._group = group
+        self._device = device
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+        self.state = PIC_State(params, markers=markers, device=device, shard=(self.rank, self.world))
+        self.nf = self.state.nf
+        if self.world > 1:
+            self._stream = torch.cuda.ExternalStream(self.state.stream(), device=device)
+            self._dens = torch.as_tensor(_DevVector(self.state.density_ptr(), 2 * self.nf),
+                                         device=f"cuda:{device}")
+
+    def step(self, dt, nsteps=1):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            self.state.step(dt, nsteps)
+            return
+        with torch.cuda.stream(self._stream):      # collectives are ordered after the stage kernels
+            for _ in range(nsteps):
+                for stage in range(3):
+                    self.state.stage_begin(dt, stage)
+                    dist.all_reduce(self._dens, op=dist.ReduceOp.SUM, group=self._group)
+                    self.state.stage_finish(stage)
+
+    def synchronize(self):
+        import torch
+        torch.cuda.synchronize(self._device)
+
+    def current_field(self):
+        return self.state.current_field()
+
+    def field_history(self, first=0, count=None):
+        return self.state.field_history(first, count)
+
+    def markers(self):
+        """(eta, weight) of this rank's block, in the caller's marker order."""
+        return self.state.markers()
+
+    def close(self):
+        self.state.close()
 
 
 class _DevMatrix:

@@ -32,3 +32,4 @@ def test_sharded_solver_matches_single_gpu(case, native_lib):
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "same_matrix=False" not in r.stdout and "same_omega=False" not in r.stdout
+    assert "same_pic=True" in r.stdout and "same_pic=False" not in r.stdout

@@ -70,6 +70,21 @@ def _worker(rank, world, port, out):
         t = torch.from_numpy(share)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ok = bool(np.array_equal(t.numpy(), full))
+        # PIC exchange emulation: every rank deposits its contiguous block of markers with the
+        # linear weights of solve_field; the all-reduce(sum) of the densities is the full deposit
+        rng = np.random.default_rng(5)
+        nmk, nf = 1001, 16
+        u = rng.uniform(0, nf, nmk)
+        wgt = rng.normal(size=nmk)
+        cell = u.astype(np.int64)
+        frac = u - cell
+        full_d = np.bincount(cell, wgt * (1 - frac), nf) + np.bincount((cell + 1) % nf, wgt * frac, nf)
+        first, count = parallel.marker_shard(nmk, rank, world)
+        sl = slice(first, first + count)
+        mine_d = torch.from_numpy(np.bincount(cell[sl], (wgt * (1 - frac))[sl], nf) +
+                                  np.bincount((cell[sl] + 1) % nf, (wgt * frac)[sl], nf))
+        dist.all_reduce(mine_d, op=dist.ReduceOp.SUM)
+        ok = ok and bool(np.allclose(mine_d.numpy(), full_d, rtol=1e-13, atol=1e-13))
         # max-over-ranks timing reduction used by bench.py
         ms = torch.tensor([10.0 + rank])
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -87,6 +102,15 @@ def test_gloo_world2_gather_and_allreduce(tmp_path):
     merged = res["merged"]
     assert [m["iters"] for m in merged] == [1, 2, 3, 4, 5, 6, 7]
     assert [m["rank"] for m in merged] == [0, 1, 0, 1, 0, 1, 0]
+
+
+def test_marker_shard_partition_is_exact():
+    for n in (1, 7, 1024, 1048576 + 5):
+        for world in (1, 2, 3, 8):
+            blocks = [parallel.marker_shard(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
+            assert all(blocks[r][0] + blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
 
 
 def test_gather_without_process_group_is_identity():
