@@ -177,6 +177,14 @@ def bench_reference(args, rank, world):
                          "sample": desc + f"; {spent:.1f} s of CPU wall time measured over {args.steps} steps"},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if PIC_DRIVER.exists():      # row N4: the reference's PIC method on the same host cores, 4 of 180 steps
+        r = subprocess.run([str(PIC_DRIVER), "time", str(PIC_PATH), "1", "4"], capture_output=True, text=True,
+                           timeout=600)
+        if r.returncode == 0:
+            c = json.loads(r.stdout.strip().splitlines()[-1])
+            line["pic"] = {"workload": "input-example.json as shipped (method PIC), 4 of 180 steps",
+                           "marker_stages_per_s": c["marker_stages_per_s"], "cores": c["threads"],
+                           "markers": c["markers"], "seconds": c["seconds"]}
     print(json.dumps(line))
 
 

@@ -33,6 +33,7 @@
 // different (and run-to-run varying) order, Bessel J comes from the Miller recurrence (abs. error
 // < 1e-15; libstdc++'s cyl_bessel_j is within 7e-15 of it) and the velocity is evaluated in
 // factored form; fields agree with the reference to ~1e-13 relative (tests/test_pic_gpu.py).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -53,6 +54,7 @@
 
 namespace {
 
+namespace cg = cooperative_groups;
 using emme::d2;
 using emme::mk2;
 using emme::PicConst;
@@ -149,25 +151,10 @@ __global__ void pic_init_kernel(PicDev d) {
 #define PIC_LB_BLOCKS 1
 #endif
 
-// One Runge-Kutta stage for every marker.  h = coef[stage][stage+1] * dt; the stage's velocity
-// combination is v = k0 (stage 0), k1 (stage 1), c1 k1 + c2 k2 (stage 2).
-template <bool SWITCH, bool SMEM>
-__global__ void __launch_bounds__(PIC_LB_THREADS, PIC_LB_BLOCKS) pic_stage_kernel(PicDev d, int stage, double h, double c1,
-                                                        double c2) {
-    extern __shared__ d2 smem[];
-    d2* s_field = smem;
-    d2* s_dens = smem + d.nf;
-    if (stage == 0 && blockIdx.x == 0 && threadIdx.x == 0) *d.step += 1;
-    if (SMEM) {
-        for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
-            s_field[i] = d.field[i];
-            s_dens[i] = mk2(0.0, 0.0);
-        }
-        __syncthreads();
-    }
-    const d2* fld = SMEM ? s_field : d.field;
-    d2* cells = SMEM ? s_dens : d.dens;
-    const int nf = d.nf;
+// The marker loop of one Runge-Kutta stage (grid-stride, one marker per thread and trip).
+template <bool SWITCH>
+__device__ __forceinline__ void stage_markers(const PicDev& d, const d2* fld, d2* cells, int stage, double h,
+                                              double c1, double c2) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < d.n; i += (long)gridDim.x * blockDim.x) {
         double eta = d.eta[i];
         d2 w = d.w[i];
@@ -202,11 +189,95 @@ __global__ void __launch_bounds__(PIC_LB_THREADS, PIC_LB_BLOCKS) pic_stage_kerne
         d.B[i] = Bn;
         if (!SWITCH) d.c[i] = cn;
     }
+}
+
+// One Runge-Kutta stage for every marker.  h = coef[stage][stage+1] * dt; the stage's velocity
+// combination is v = k0 (stage 0), k1 (stage 1), c1 k1 + c2 k2 (stage 2).
+template <bool SWITCH, bool SMEM>
+__global__ void __launch_bounds__(PIC_LB_THREADS, PIC_LB_BLOCKS) pic_stage_kernel(PicDev d, int stage, double h, double c1,
+                                                        double c2) {
+    extern __shared__ d2 smem[];
+    d2* s_field = smem;
+    d2* s_dens = smem + d.nf;
+    if (stage == 0 && blockIdx.x == 0 && threadIdx.x == 0) *d.step += 1;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
+            s_field[i] = d.field[i];
+            s_dens[i] = mk2(0.0, 0.0);
+        }
+        __syncthreads();
+    }
+    const d2* fld = SMEM ? s_field : d.field;
+    d2* cells = SMEM ? s_dens : d.dens;
+    const int nf = d.nf;
+    stage_markers<SWITCH>(d, fld, cells, stage, h, c1, c2);
     if (SMEM) {
         __syncthreads();
         d2* mine = d.part + (size_t)blockIdx.x * nf;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) mine[i] = s_dens[i];
     }
+}
+
+// nsteps x Integrator::step in ONE cooperative launch (shared-memory cells only): the grid-wide
+// barrier replaces the kernel boundaries.  Per stage: marker loop -> partial store -> grid.sync ->
+// every CTA reduces its slice of cells over all partials (32 chunks per cell, fixed order), applies
+// the quasi-neutrality table, writes the field (and the history after stage 2) -> grid.sync.
+template <bool SWITCH>
+__global__ void __launch_bounds__(PIC_LB_THREADS, PIC_LB_BLOCKS) pic_persistent_kernel(PicDev d, double dt, int nsteps,
+                                                                        unsigned long long first_slot) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ d2 smem[];
+    d2* s_field = smem;
+    d2* s_dens = smem + d.nf;
+    __shared__ d2 red[PIC_FIELD_CHUNKS][32];
+    const int nf = d.nf;
+    const double RK[4][4] = EMME_PIC_RK_COEF;   // only constant indices below: folded at compile time
+    const int cpc = (nf + gridDim.x - 1) / gridDim.x;             // cells per CTA in the reduce
+    const int c_begin = blockIdx.x * cpc, c_end = min(c_begin + cpc, nf);
+    const int lane_cell = threadIdx.x & 31, ch = threadIdx.x >> 5;   // 32 cells x up to 32 chunks
+    const int nch = min((int)(blockDim.x >> 5), PIC_FIELD_CHUNKS);
+    for (int step = 0; step < nsteps; ++step) {
+        for (int stage = 0; stage < 3; ++stage) {
+            for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+                const double2 f = __ldcg(reinterpret_cast<const double2*>(&d.field[i]));
+                s_field[i] = mk2(f.x, f.y);
+                s_dens[i] = mk2(0.0, 0.0);
+            }
+            __syncthreads();
+            const double hfac = stage == 0 ? RK[0][1] : (stage == 1 ? RK[1][2] : RK[2][3]);
+            stage_markers<SWITCH>(d, s_field, s_dens, stage, hfac * dt, RK[2][1], RK[2][2]);
+            __syncthreads();
+            d2* mine = d.part + (size_t)blockIdx.x * nf;
+            for (int i = threadIdx.x; i < nf; i += blockDim.x) mine[i] = s_dens[i];
+            grid.sync();
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                const int cell = c0 + lane_cell;
+                d2 acc = mk2(0.0, 0.0);
+                if (cell < c_end && ch < nch) {
+                    for (int g = ch; g < (int)gridDim.x; g += nch) {
+                        const double2 v = __ldcg(reinterpret_cast<const double2*>(&d.part[(size_t)g * nf + cell]));
+                        acc.x += v.x;
+                        acc.y += v.y;
+                    }
+                }
+                if (ch < PIC_FIELD_CHUNKS) red[ch][lane_cell] = acc;
+                __syncthreads();
+                if (ch == 0 && cell < c_end) {
+                    for (int c = 1; c < nch; ++c) {
+                        acc.x += red[c][lane_cell].x;
+                        acc.y += red[c][lane_cell].y;
+                    }
+                    const double cf = d.coef[cell];
+                    const d2 f = mk2(acc.x * cf, acc.y * cf);
+                    d.field[cell] = f;
+                    if (stage == 2) d.hist[(first_slot + step) * (unsigned long long)nf + cell] = f;
+                }
+                __syncthreads();
+            }
+            grid.sync();
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d.step = first_slot + nsteps;
 }
 
 const double RK_COEF[4][4] = EMME_PIC_RK_COEF;
@@ -235,6 +306,11 @@ struct emme_pic {
     cudaGraphExec_t graph = nullptr;
     double graph_dt = 0;
     int use_graph = 1;
+    // one cooperative launch per emme_pic_step call (grid.sync instead of kernel boundaries):
+    // measured slower than the graph (40.2 vs 38.9 us/stage at 1M markers, 21.3 vs 14.3 at 64K), kept
+    // as a tested alternative behind EMME_PIC_PERSISTENT=1
+    int use_persistent = 0;
+    int pgrid = 0;
     double last_ms = 0;
     unsigned long long launches = 0;
 };
@@ -339,7 +415,12 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     if (emme_device_count() <= 0)
         return capi_fail(EMME_E_NO_DEVICE, "no CUDA device: emme_b200 has no CPU fallback");
     CU(cudaSetDevice(device));
-    emme_pic* s = new emme_pic();
+    // released by the guard on every early return below
+    struct Guard {
+        emme_pic* h;
+        ~Guard() { if (h) emme_pic_destroy(h); }
+    } guard{new emme_pic()};
+    emme_pic* s = guard.h;
     s->device = device;
     s->p = *p;
     s->n_total = n_total;
@@ -479,6 +560,23 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     const long want = (n + s->block - 1) / s->block;
     const long cap = (long)s->sms * per_sm;
     s->grid = (int)(want < cap ? want : cap);
+    if (const char* e = std::getenv("EMME_PIC_PERSISTENT")) s->use_persistent = std::atoi(e);
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!d.use_smem || !coop || shard_count > 1) s->use_persistent = 0;
+    if (s->use_persistent) {
+        const void* pfn = sw ? (const void*)pic_persistent_kernel<true> : (const void*)pic_persistent_kernel<false>;
+        CU(cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+        int pper = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pper, pfn, s->block, s->smem));
+        if (pper < 1) {
+            s->use_persistent = 0;
+        } else {
+            const long pcap = (long)s->sms * pper;
+            s->pgrid = (int)(want < pcap ? want : pcap);
+            if (s->pgrid > s->grid) s->grid = s->pgrid;   // one partial buffer serves both paths
+        }
+    }
     d.nparts = d.use_smem ? s->grid : 0;
     CU(dev_alloc(&d.part, (size_t)d.nparts * nf));
     if (const char* e = std::getenv("EMME_PIC_GRAPH")) s->use_graph = std::atoi(e);
@@ -489,6 +587,7 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
+    guard.h = nullptr;
     *out = s;
     return 0;
 }
@@ -522,6 +621,22 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
         return capi_fail(EMME_E_STATE, "sharded PIC state: use emme_pic_stage_begin/finish around the density exchange");
     CU(cudaSetDevice(s->device));
     if (int rc = ensure_history(s, s->steps_done + nsteps)) return rc;
+    if (s->use_persistent && nsteps > 0) {
+        const bool sw = s->p.drift_center_transformation_switch != 0;
+        const void* pfn = sw ? (const void*)pic_persistent_kernel<true> : (const void*)pic_persistent_kernel<false>;
+        unsigned long long first_slot = (unsigned long long)s->steps_done;
+        void* args[] = {&s->d, &dt, &nsteps, &first_slot};
+        CU(cudaEventRecord(s->ev0, s->stream));
+        CU(cudaLaunchCooperativeKernel(pfn, dim3(s->pgrid), dim3(s->block), args, s->smem, s->stream));
+        s->launches++;
+        CU(cudaEventRecord(s->ev1, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        float pms = 0;
+        CU(cudaEventElapsedTime(&pms, s->ev0, s->ev1));
+        s->last_ms = pms;
+        s->steps_done += nsteps;
+        return 0;
+    }
     if (s->use_graph && nsteps > 0 && (!s->graph || s->graph_dt != dt)) {
         if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
         cudaGraph_t g = nullptr;

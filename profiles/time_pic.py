@@ -17,7 +17,7 @@ markers = pic.load_markers(p, mpc * p.npoints, seed=1)
 t1 = time.perf_counter()
 s = pic.PIC_State.from_markers(p, *markers)
 t2 = time.perf_counter()
-s.step(dt, 3)   # warm-up (graph capture)
+s.step(dt, 3)   # warm-up (graph capture unless EMME_PIC_PERSISTENT=1)
 ms = []
 for _ in range(3):
     s.step(dt, steps)

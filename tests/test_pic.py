@@ -75,6 +75,29 @@ def test_pic_input_keys(native_lib):
         pic.pic_params(Input(text=open(cases.GOLD / "inputs" / "pic.json").read().replace("marker_per_cell", "mpc")))
 
 
+def test_pic_argument_errors_are_lapack_style(native_lib):
+    """0 ok, -k = argument k illegal (include/emme_b200.h), checked before any device is needed."""
+    import ctypes
+    g, p, _, _ = load_case("n32")
+    dp = ctypes.POINTER(ctypes.c_double)
+    a = np.zeros(8)
+    ptr = a.ctypes.data_as(dp)
+    L = native_lib
+    assert L.emme_pic_load_markers(None, 4, 1, ptr, ptr, ptr, ptr) == -1
+    assert L.emme_pic_load_markers(ctypes.byref(p), -1, 1, ptr, ptr, ptr, ptr) == -2
+    assert L.emme_pic_load_markers(ctypes.byref(p), 2, 1, None, ptr, ptr, ptr) == -4
+    h = ctypes.c_void_p()
+    assert L.emme_pic_create(None, 4, ptr, ptr, ptr, ptr, 0, ctypes.byref(h)) == -1
+    assert L.emme_pic_create(ctypes.byref(p), 0, ptr, ptr, ptr, ptr, 0, ctypes.byref(h)) == -2
+    assert L.emme_pic_create(ctypes.byref(p), 4, None, ptr, ptr, ptr, 0, ctypes.byref(h)) == -3
+    assert L.emme_pic_create_shard(ctypes.byref(p), 4, ptr, ptr, ptr, ptr, 2, 2, 0, ctypes.byref(h)) == -7
+    assert L.emme_pic_step(None, 0.25, 1) == -1 and L.emme_pic_current_field(None, None) == -1
+    re, im = ctypes.c_double(), ctypes.c_double()
+    assert L.emme_pic_calculate_omega(ptr, 2, 0.25, ctypes.byref(re), ctypes.byref(im)) == -2
+    assert b"four steps" in L.emme_last_error()
+    assert L.emme_pic_destroy(None) == 0 and L.emme_pic_marker_num(None) == -1
+
+
 def test_pic_no_cpu_fallback(native_lib):
     if native_lib.emme_device_count() > 0:
         pytest.skip("a CUDA device is present")

@@ -21,9 +21,12 @@ def load_case(case):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("graph", [1, 0])
-def test_fields_match_reference(case, graph, native_lib, monkeypatch):
-    monkeypatch.setenv("EMME_PIC_GRAPH", str(graph))
+@pytest.mark.parametrize("mode", ["persistent", "graph", "launches"])
+def test_fields_match_reference(case, mode, native_lib, monkeypatch):
+    """All three ways emme_pic_step drives the device: a CUDA graph of the six launches of a step
+    (default), plain launches, one cooperative launch for the whole call (EMME_PIC_PERSISTENT=1)."""
+    monkeypatch.setenv("EMME_PIC_PERSISTENT", "1" if mode == "persistent" else "0")
+    monkeypatch.setenv("EMME_PIC_GRAPH", "1" if mode == "graph" else "0")
     g, p, _, dt = load_case(case)
     steps = int(g["steps"])
     s = pic.PIC_State.from_markers(p, g["eta"], g["v_para"], g["v_perp"], g["weight"])
@@ -52,8 +55,8 @@ def test_fields_match_reference(case, graph, native_lib, monkeypatch):
     om, ref_om = pic.calculate_omega(stats, dt), complex(g["omega"][0])
     assert abs(om - ref_om) <= 1e-8 * abs(ref_om)
     _, launches = s.timing()
-    assert launches >= 3 * steps
-    print(f"pic {case} graph={graph}: worst field deviation {worst:.2e}, weights {werr:.2e}, launches {launches}")
+    assert launches >= (3 if mode == "persistent" else 6 * steps)
+    print(f"pic {case} {mode}: worst field deviation {worst:.2e}, weights {werr:.2e}, launches {launches}")
     s.close()
 
 
