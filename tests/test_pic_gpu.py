@@ -60,6 +60,37 @@ def test_fields_match_reference(case, mode, native_lib, monkeypatch):
     s.close()
 
 
+def test_edge_cases(native_lib):
+    """Zero steps, ragged marker counts (1 marker, a prime count), history range errors, a time step
+    change between calls (new graph), a single very fast marker (several domain lengths per stage)."""
+    from emme_b200 import EmmeError
+    g, p, _, dt = load_case("n32")
+    for n in (1, 997):
+        m = [np.ascontiguousarray(g[k][:n]) for k in ("eta", "v_para", "v_perp", "weight")]
+        if n == 1:
+            m[1] = np.array([4000.0])          # crosses the domain ~14 times per stage: fmod branch
+        s = pic.PIC_State.from_markers(p, *m)
+        o = O.PicOracle(p.as_dict(), *m)
+        s.step(dt, 0)
+        assert s.steps_done() == 0 and s.field_history().shape == (0, p.npoints)
+        with pytest.raises(EmmeError, match="outside the recorded history"):
+            s.field_history(0, 1)
+        for h in (dt, dt, 0.5 * dt):
+            s.step(h)
+            o.step(h)
+            ref = o.field()
+            assert np.abs(s.current_field() - ref).max() <= FIELD_TOL * np.abs(ref).max()
+        eta, w = s.markers()
+        oeta, ow = o.markers()
+        assert np.array_equal(eta, oeta) and np.abs(w - ow).max() <= FIELD_TOL * np.abs(ow).max()
+        assert s.steps_done() == 3 and s.field_history(1, 2).shape == (2, p.npoints)
+        s.close()
+    with pytest.raises(EmmeError):
+        bad = type(p).from_buffer_copy(p)
+        bad.npoints = 2
+        pic.PIC_State.from_markers(bad, g["eta"], g["v_para"], g["v_perp"], g["weight"])
+
+
 def test_against_oracle_seeded_1k_cells(native_lib):
     """A case no fixture holds: 128 cells x 64 markers, markers drawn by the product's own loader,
     the C restatement stepped beside the GPU."""
