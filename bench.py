@@ -259,7 +259,7 @@ def bench_pic(device, hbm_peak):
     n = mpc * p.npoints
     out["e2e"] = {"seconds": t1 - t0, "marker_stages_per_s": 3.0 * n * nt / (t1 - t0),
                   "h2d_bytes": 48 * n, "d2h_bytes": 16 * p.npoints * nt,
-                  "eigenvalue": res["eigenvalue"],
+                  "eigenvalue": res["eigenvalue"], "breakdown": res["timing"],
                   "note": "solve_once_pic: std::mt19937 marker loading and v_perp sort on one host core, upload, "
                           "all steps, field history download, util::calculate_omega; the eigen method gives "
                           "omega = (-0.8235, 0.2585) for the same physics (the PIC frequency carries no sign)"}

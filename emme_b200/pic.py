@@ -159,14 +159,22 @@ def solve_once_pic(inp, seed=-1, device=0, field_file=None):
     """src/main.cpp:82-137: step_number steps of time_step, the field of every step appended to
     field_file (eigenMatrics/*.bin), eigenvalue from util::calculate_omega, eigenvector = the last
     field."""
+    import time
     p, mpc, nt, dt = pic_params(inp)
-    state = PIC_State(p, mpc, seed=seed, device=device)
+    t0 = time.perf_counter()
+    markers = load_markers(p, int(mpc) * p.npoints, seed)
+    t1 = time.perf_counter()
+    state = PIC_State(p, markers=markers, device=device)
+    t2 = time.perf_counter()
     state.step(dt, nt)
+    t3 = time.perf_counter()
     if field_file is not None:
         state.field_history().tofile(field_file)
     stats = state.field_stats()
     omega = calculate_omega(stats, dt)
     result = {"eigenvalue": [omega.real, omega.imag], "eigenvector": state.current_field(), "stats": stats,
-              "step_ms": state.timing()[0] / max(nt, 1), "markers": state.marker_num()}
+              "step_ms": state.timing()[0] / max(nt, 1), "markers": state.marker_num(),
+              "timing": {"load_markers_s": t1 - t0, "create_upload_s": t2 - t1, "steps_s": t3 - t2,
+                         "diagnostics_s": time.perf_counter() - t3}}
     state.close()
     return result
