@@ -151,15 +151,38 @@ __global__ void pic_init_kernel(PicDev d) {
 #define PIC_LB_BLOCKS 1
 #endif
 
+// L1 prefetch of the marker a thread handles in its NEXT trip: costs no registers, and the loads at
+// the top of the next trip (the kernel's largest stall in the first profile) find their lines
+#ifndef PIC_PREFETCH
+#define PIC_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#if PIC_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
 // The marker loop of one Runge-Kutta stage (grid-stride, one marker per thread and trip).
 template <bool SWITCH>
 __device__ __forceinline__ void stage_markers(const PicDev& d, const d2* fld, d2* cells, int stage, double h,
                                               double c1, double c2) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < d.n; i += (long)gridDim.x * blockDim.x) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < d.n; i += stride) {
         double eta = d.eta[i];
         d2 w = d.w[i];
         const d2 A = d.A[i], B = d.B[i];
         const double vpar = d.vpar[i], vperp = d.vperp[i], pw = d.pw[i];
+        if (i + stride < d.n) {
+            const long nx = i + stride;
+            prefetch_l1(&d.eta[nx]);
+            prefetch_l1(&d.w[nx]);
+            prefetch_l1(&d.A[nx]);
+            prefetch_l1(&d.B[nx]);
+            prefetch_l1(&d.vpar[nx]);
+            prefetch_l1(&d.vperp[nx]);
+            prefetch_l1(&d.pw[nx]);
+            if (stage == 2) prefetch_l1(&d.k1[nx]);
+        }
         // gather + velocity of this stage (include/solver_pic.h:91-121)
         d2 vs = emme::pic_velocity(d.k, fld, eta, A, B);
         if (!SWITCH) {  // -weight omega_d omega_dv i (include/solver_pic.h:112-114)
