@@ -37,10 +37,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <numeric>
 #include <random>
 #include <string>
@@ -349,9 +351,25 @@ using emme::capi_fail;
             return capi_fail(EMME_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
     } while (0)
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with a release
+// threshold of 8 GiB: a scan creates and destroys one PIC state per scan point, and plain
+// cudaMalloc/cudaFree of the ~15 buffers cost 0.15-0.6 s per state (measured, EMME_PIC_TIMING=1)
+// against 24 ms for the 180 steps themselves.
 template <typename T>
-cudaError_t dev_alloc(T** p, size_t count) {
-    return cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1));
+cudaError_t dev_alloc(T** p, size_t count, cudaStream_t stream) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1), stream);
+}
+
+cudaError_t configure_pool(int device) {
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e != cudaSuccess) return e;
+    unsigned long long cur = 0;
+    e = cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+    if (e != cudaSuccess) return e;
+    unsigned long long want = 8ULL << 30;
+    if (cur >= want) return cudaSuccess;
+    return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
 }
 
 int ensure_history(emme_pic* s, long steps_total) {
@@ -359,13 +377,13 @@ int ensure_history(emme_pic* s, long steps_total) {
     long cap = s->hist_cap ? s->hist_cap : 256;
     while (cap < steps_total) cap *= 2;
     d2* nh = nullptr;
-    CU(dev_alloc(&nh, (size_t)cap * s->d.nf));
+    CU(dev_alloc(&nh, (size_t)cap * s->d.nf, s->stream));
     if (s->d.hist && s->steps_done > 0) {
         CU(cudaMemcpyAsync(nh, s->d.hist, sizeof(d2) * (size_t)s->steps_done * s->d.nf,
                            cudaMemcpyDeviceToDevice, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
-    if (s->d.hist) CU(cudaFree(s->d.hist));
+    if (s->d.hist) CU(cudaFreeAsync(s->d.hist, s->stream));
     s->d.hist = nh;
     s->hist_cap = cap;
     if (s->graph) {  // the captured launches hold the old pointer
@@ -455,17 +473,34 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     const long n = s->n, f0 = s->first;
     const int nf = p->npoints;
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
+    CU(configure_pool(device));
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
 
+    // EMME_PIC_TIMING=1 prints the host phases of this call to stderr
+    const bool timing = std::getenv("EMME_PIC_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tprev = tnow();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto t = tnow();
+        std::fprintf(stderr, "[emme_pic_create] %-28s %8.3f ms\n", what,
+                     std::chrono::duration<double, std::milli>(t - tprev).count());
+        tprev = t;
+    };
+    lap("stream + events");
     // initialize_marker_extras (include/solver_pic.h:207-238): p_weight normalised over ALL markers
     std::vector<double> pw(n_total);
-    for (long i = 0; i < n_total; ++i) {
-        const double vp = v_para[i], vq = v_perp[i];
-        pw[i] = vq * std::exp(-(vp * vp * (1 - p->water_bag_weight_vpara) +
-                                vq * vq * (1 - p->water_bag_weight_vperp)) /
-                              (2 * p->vt * p->vt));
+    const double wa = 1 - p->water_bag_weight_vpara, wb = 1 - p->water_bag_weight_vperp;
+    if (wa == 0 && wb == 0) {
+        // the exponent is -0/(2 vt^2): exp gives exactly 1 for every finite marker, v_perp * 1 = v_perp
+        for (long i = 0; i < n_total; ++i) pw[i] = v_perp[i];
+    } else {
+        for (long i = 0; i < n_total; ++i) {
+            const double vp = v_para[i], vq = v_perp[i];
+            pw[i] = vq * std::exp(-(vp * vp * wa + vq * vq * wb) / (2 * p->vt * p->vt));
+        }
     }
     double sum = 0;
     for (long i = 0; i < n_total; ++i) sum += pw[i];
@@ -483,6 +518,7 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
         s->h_coef[idx] = 1. / ((1. + 1. / p->tau - g0) * cell_width);
     }
 
+    lap("extras + table (host)");
     PicDev& d = s->d;
     d.n = n;
     d.nf = nf;
@@ -501,21 +537,22 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     k.eta_i = p->eta_i;
     k.inv_2vt2 = 1.0 / (2. * p->vt * p->vt);
     double *dvpar, *dvperp, *dpw, *dcoef;
-    CU(dev_alloc(&d.eta, n));
-    CU(dev_alloc(&dvpar, n));
-    CU(dev_alloc(&dvperp, n));
-    CU(dev_alloc(&dpw, n));
-    CU(dev_alloc(&d.w, n));
-    CU(dev_alloc(&d.A, n));
-    CU(dev_alloc(&d.B, n));
-    CU(dev_alloc(&d.k1, n));
-    CU(dev_alloc(&d.c, p->drift_center_transformation_switch ? 1 : n));
-    CU(dev_alloc(&d.field, nf));
-    CU(dev_alloc(&d.dens, nf));
-    CU(dev_alloc(&dcoef, nf));
-    CU(dev_alloc(&d.step, 1));
+    CU(dev_alloc(&d.eta, n, s->stream));
+    CU(dev_alloc(&dvpar, n, s->stream));
+    CU(dev_alloc(&dvperp, n, s->stream));
+    CU(dev_alloc(&dpw, n, s->stream));
+    CU(dev_alloc(&d.w, n, s->stream));
+    CU(dev_alloc(&d.A, n, s->stream));
+    CU(dev_alloc(&d.B, n, s->stream));
+    CU(dev_alloc(&d.k1, n, s->stream));
+    CU(dev_alloc(&d.c, p->drift_center_transformation_switch ? 1 : n, s->stream));
+    CU(dev_alloc(&d.field, nf, s->stream));
+    CU(dev_alloc(&d.dens, nf, s->stream));
+    CU(dev_alloc(&dcoef, nf, s->stream));
+    CU(dev_alloc(&d.step, 1, s->stream));
     d.vpar = dvpar; d.vperp = dvperp; d.pw = dpw; d.coef = dcoef;
     s->d_vpar = dvpar; s->d_vperp = dvperp; s->d_pw = dpw; s->d_coef = dcoef;
+    lap("cudaMalloc");
     // Device order: markers sorted by v_perp.  The Miller recurrence of bessel_j01 runs
     // ~ x + 12.6 x^(1/3) trips with x = (v_perp/vt) sb(eta); lanes of a warp that share v_perp
     // differ only through sb(eta), which halves the spread of trip counts inside a warp.  The
@@ -539,8 +576,12 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
         for (int b = 0; b < NB; ++b) start[b + 1] += start[b];
         for (long i = 0; i < n; ++i) s->perm[start[bucket[i]]++] = i;
     }
+    lap("counting sort (host)");
     {
-        std::vector<double> t_eta(n), t_vpar(n), t_vperp(n), t_pw(n), t_w(2 * (size_t)n);
+        // one uninitialised staging block (a zero-filled std::vector costs a second pass over 48 B/marker)
+        std::unique_ptr<double[]> stage(new double[6 * (size_t)n]);
+        double *t_eta = stage.get(), *t_vpar = t_eta + n, *t_vperp = t_vpar + n, *t_pw = t_vperp + n,
+               *t_w = t_pw + n;
         for (long j = 0; j < n; ++j) {
             const long i = f0 + s->perm[j];
             t_eta[j] = eta[i];
@@ -550,12 +591,13 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
             t_w[2 * j] = weight[2 * i];
             t_w[2 * j + 1] = weight[2 * i + 1];
         }
-        CU(cudaMemcpyAsync(d.eta, t_eta.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(dvpar, t_vpar.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(dvperp, t_vperp.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(dpw, t_pw.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(d.w, t_w.data(), sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(d.eta, t_eta, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dvpar, t_vpar, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dvperp, t_vperp, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dpw, t_pw, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(d.w, t_w, sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
         CU(cudaStreamSynchronize(s->stream));   // the staging vectors go out of scope
+        lap("permute + upload");
     }
     CU(cudaMemcpyAsync(dcoef, s->h_coef.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemsetAsync(d.field, 0, sizeof(d2) * nf, s->stream));
@@ -601,7 +643,7 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
         }
     }
     d.nparts = d.use_smem ? s->grid : 0;
-    CU(dev_alloc(&d.part, (size_t)d.nparts * nf));
+    CU(dev_alloc(&d.part, (size_t)d.nparts * nf, s->stream));
     if (const char* e = std::getenv("EMME_PIC_GRAPH")) s->use_graph = std::atoi(e);
 
     const int ig = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
@@ -610,6 +652,7 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
+    lap("launch geometry + init kernel");
     guard.h = nullptr;
     *out = s;
     return 0;
@@ -626,10 +669,13 @@ int emme_pic_destroy(emme_pic* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->graph) cudaGraphExecDestroy(s->graph);
     PicDev& d = s->d;
-    cudaFree(d.eta); cudaFree(s->d_vpar); cudaFree(s->d_vperp); cudaFree(s->d_pw);
-    cudaFree(d.w); cudaFree(d.A); cudaFree(d.B); cudaFree(d.k1); cudaFree(d.c);
-    cudaFree(d.field); cudaFree(d.dens); cudaFree(s->d_coef); cudaFree(d.hist);
-    cudaFree(d.part); cudaFree(d.step);
+    if (s->stream) {   // back to the pool, stream-ordered
+        void* bufs[] = {d.eta, s->d_vpar, s->d_vperp, s->d_pw, d.w, d.A, d.B, d.k1, d.c, d.field, d.dens,
+                        s->d_coef, d.hist, d.part, d.step};
+        for (void* b : bufs)
+            if (b) cudaFreeAsync(b, s->stream);
+        cudaStreamSynchronize(s->stream);
+    }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
