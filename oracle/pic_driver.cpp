@@ -31,6 +31,12 @@
 //         omega (re, im) = util::calculate_omega(stats, dt) of solve_once_pic (src/main.cpp:124)
 //   pic_driver time <input.json> <seed> <nsteps>
 //       wall time of nsteps Integrator::step calls on all host threads (CPU baseline).
+//   pic_driver oscillator <out.bin>
+//       the reference's Integrator template on the harmonic oscillator x'' = -x of
+//       test/test_integrator.cpp (that test no longer compiles against the current header: its
+//       state lacks initial_velocity_storage(); the state below adds exactly that).  out.bin:
+//       u64 n_fixed, then (t, x0, x1) per fixed step dt = 0.01 up to t = 10; u64 n_adaptive, then
+//       (dt, t, x0, x1) per step_adaptive call with bounds 1e-5 / 1e-7 until t >= 10.
 #include <chrono>
 #include <complex>
 #include <cstdio>
@@ -38,6 +44,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <new>
 #include <numeric>
 #include <random>
@@ -71,6 +78,66 @@ struct emme_fixed_seed_device {
 using cplx = std::complex<double>;
 using State = PIC_State<double>;
 
+// test/test_integrator.cpp's double_state with the one member the current Integrator needs
+struct double_state {
+    using value_type = double;
+    struct velocity_type {
+        value_type v0, v1;
+    };
+    friend auto operator*(value_type a, velocity_type v) { return velocity_type{a * v.v0, a * v.v1}; }
+    friend auto operator+(velocity_type lhs, velocity_type rhs) {
+        return velocity_type{lhs.v0 + rhs.v0, lhs.v1 + rhs.v1};
+    }
+    velocity_type initial_velocity_storage() const { return velocity_type{}; }
+    void put_velocity(velocity_type& v) {
+        v.v0 = x1;
+        v.v1 = -x0;
+    }
+    void update(velocity_type v, value_type dt) {
+        x0 += v.v0 * dt;
+        x1 += v.v1 * dt;
+        t += dt;
+    }
+    auto get_update_err(velocity_type v, value_type dt) {
+        auto l2 = [](value_type a, value_type b) { return std::sqrt(.5 * (a * a + b * b)); };
+        return l2(x0, x1) < std::numeric_limits<value_type>::epsilon() ? l2(v.v0 * dt, v.v1 * dt)
+                                                                        : l2(v.v0 * dt, v.v1 * dt) / l2(x0, x1);
+    }
+    double t;
+    double x0, x1;
+};
+
+static int run_oscillator(const char* path) {
+    std::ofstream f(path, std::ios::binary);
+    constexpr double total_t = 10;
+    {
+        double_state x2{0, 0, 1};
+        Integrator<double_state> f2(x2, 1.e-5, 1.e-7);
+        constexpr double dt = 0.01;
+        const std::uint64_t n = static_cast<std::uint64_t>(total_t / dt);
+        f.write(reinterpret_cast<const char*>(&n), 8);
+        for (std::size_t i = 0; i < total_t / dt; ++i) {
+            f2.step(dt);
+            const double rec[3] = {x2.t, x2.x0, x2.x1};
+            f.write(reinterpret_cast<const char*>(rec), sizeof(rec));
+        }
+    }
+    {
+        double_state x2{0, 0, 1};
+        Integrator<double_state> f2(x2, 1.e-5, 1.e-7);
+        std::vector<std::array<double, 4>> recs;
+        while (x2.t < total_t) {
+            auto dt = f2.step_adaptive();
+            recs.push_back({dt, x2.t, x2.x0, x2.x1});
+        }
+        const std::uint64_t n = recs.size();
+        f.write(reinterpret_cast<const char*>(&n), 8);
+        f.write(reinterpret_cast<const char*>(recs.data()), sizeof(recs[0]) * recs.size());
+        std::printf("oscillator: %zu adaptive steps\n", recs.size());
+    }
+    return f ? 0 : 4;
+}
+
 static util::json::Value load_input(const std::string& path) {
     auto input_all = util::json::parse_file(path);
     auto input = input_all.clone();
@@ -86,6 +153,7 @@ static void put(std::ofstream& f, const T* p, std::size_t n) {
 }
 
 int main(int argc, char** argv) {
+    if (argc == 3 && std::string(argv[1]) == "oscillator") return run_oscillator(argv[2]);
     if (argc < 5) {
         std::fprintf(stderr, "usage: pic_driver run|time <input.json> <seed> <nsteps> [out.bin]\n");
         return 2;

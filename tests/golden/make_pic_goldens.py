@@ -4,7 +4,8 @@
 Run in the build container only: needs oracle/_ref/pic_driver (oracle/Makefile `make ref`, the
 reference's include/solver_pic.h with a reproducible seed, see oracle/pic_driver.cpp).  Writes
 tests/golden/pic_<case>.npz: the loaded markers, the derived tables, the field after every
-Integrator::step, the final marker state and util::calculate_omega of the run.
+Integrator::step, the final marker state and util::calculate_omega of the run; and
+tests/golden/oscillator_rk3.bin: the Integrator template on x'' = -x (fixed and adaptive steps).
 """
 import subprocess
 import sys
@@ -58,6 +59,8 @@ def main():
             d = {k: d[k] for k in ("fields", "omega")}
         np.savez_compressed(HERE / f"pic_{case}.npz", seed=seed, steps=steps, input=inp, **d)
         print(case, {k: v.shape for k, v in d.items()}, d["omega"])
+    # the reference's Integrator template on the oscillator of test/test_integrator.cpp
+    subprocess.run([str(DRIVER), "oscillator", str(HERE / "oscillator_rk3.bin")], check=True)
 
 
 if __name__ == "__main__":
