@@ -25,14 +25,17 @@
 //            into the new field (quasi-neutrality table, :349-351); after stage 2 it appends the
 //            field to the on-device history that the diagnostics read.
 // Six launches per Integrator::step, captured once per dt into a CUDA graph and replayed.
-// (The first version flushed the cells with red.global.add.f64 and let the last CTA form the
-// field: 592 CTAs adding into the same 128 cache lines serialised at ~8 cycles per atomic and
-// line, 20 of 49 us per stage at 1M markers; see DESIGN.md.)
+// (The first version flushed the cells with red.global.add.f64 and let the last CTA -- a ticket --
+// form the field in the same launch.  At equal block size it measured within 1 us per stage of this
+// one; the partial-sum form is kept because its reduction order is fixed.  What did matter is the
+// CTA size: one 1024-thread CTA per SM instead of four 256-thread ones, 49 -> 39 us per stage at
+// 1M markers.  See DESIGN.md section 4c.)
 //
 // Differences to the reference that are visible in the numbers: deposits are summed in a
 // different (and run-to-run varying) order, Bessel J comes from the Miller recurrence (abs. error
 // < 1e-15; libstdc++'s cyl_bessel_j is within 7e-15 of it) and the velocity is evaluated in
-// factored form; fields agree with the reference to ~1e-13 relative (tests/test_pic_gpu.py).
+// factored form; fields agree with the reference to 4e-15 of the largest field value, positions bit
+// for bit (tests/test_pic_gpu.py).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 

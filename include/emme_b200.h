@@ -1,4 +1,5 @@
-/* emme_b200.h -- C ABI of the B200-native EMME eigen hot path.
+/* emme_b200.h -- C ABI of the B200-native EMME eigen hot path (and, at the end of the file, of
+ * the reference's second method, the PIC initial-value run: emme_pic_*).
  *
  * Drop-in boundary for the one data-parallel path of ssskkkky/EMME: the assembly of
  * the eigenmatrix A(omega) and the dense step of the Newton/secant root find.  The
