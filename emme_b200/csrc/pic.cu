@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(32 * PIC_FIELD_CHUNKS) pic_field_kernel(PicDev
     const int cell = blockIdx.x * 32 + threadIdx.x, ch = threadIdx.y;
     d2 acc = mk2(0.0, 0.0);
     const bool summed = (mode == 2) || !d.use_smem;
+    cudaGridDependencySynchronize();             // the stage kernel's partials are complete and visible
+    cudaTriggerProgrammaticLaunchCompletion();   // the next stage kernel may start its prologue
     if (cell < d.nf) {
         if (summed) {
             if (ch == 0) acc = d.dens[cell];
@@ -227,12 +229,15 @@ __global__ void __launch_bounds__(PIC_LB_THREADS, PIC_LB_BLOCKS) pic_stage_kerne
     extern __shared__ d2 smem[];
     d2* s_field = smem;
     d2* s_dens = smem + d.nf;
+    // Programmatic dependent launch: this grid may start while pic_field_kernel of the previous
+    // stage is still running; everything before the dependency sync touches shared memory only.
+    if (SMEM)
+        for (int i = threadIdx.x; i < d.nf; i += blockDim.x) s_dens[i] = mk2(0.0, 0.0);
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();   // lets pic_field_kernel get resident early; it waits itself
     if (stage == 0 && blockIdx.x == 0 && threadIdx.x == 0) *d.step += 1;
     if (SMEM) {
-        for (int i = threadIdx.x; i < d.nf; i += blockDim.x) {
-            s_field[i] = d.field[i];
-            s_dens[i] = mk2(0.0, 0.0);
-        }
+        for (int i = threadIdx.x; i < d.nf; i += blockDim.x) s_field[i] = d.field[i];
         __syncthreads();
     }
     const d2* fld = SMEM ? s_field : d.field;
@@ -334,6 +339,7 @@ struct emme_pic {
     cudaGraphExec_t graph = nullptr;
     double graph_dt = 0;
     int use_graph = 1;
+    int use_pdl = 1;          // programmatic dependent launch between the kernels of a step
     // one cooperative launch per emme_pic_step call (grid.sync instead of kernel boundaries):
     // measured slower than the graph (40.2 vs 38.9 us/stage at 1M markers, 21.3 vs 14.3 at 64K), kept
     // as a tested alternative behind EMME_PIC_PERSISTENT=1
@@ -396,26 +402,40 @@ int ensure_history(emme_pic* s, long steps_total) {
     return 0;
 }
 
+// Launch with the programmatic-stream-serialisation attribute (s->use_pdl): the kernel may become
+// resident before its predecessor in the stream has finished; its cudaGridDependencySynchronize()
+// is the real dependency.  Captured into the step graph as a programmatic edge.
+template <typename... Params, typename... Args>
+cudaError_t launch_pdl(emme_pic* s, void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = s->use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    s->launches++;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 cudaError_t launch_stage(emme_pic* s, double dt, int stage) {
     const double h = RK_COEF[stage][stage + 1] * dt;
     const double c1 = RK_COEF[2][1], c2 = RK_COEF[2][2];
     const bool sw = s->p.drift_center_transformation_switch != 0;
     dim3 grid(s->grid), block(s->block);
     if (s->d.use_smem) {
-        if (sw) pic_stage_kernel<true, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2);
-        else pic_stage_kernel<false, true><<<grid, block, s->smem, s->stream>>>(s->d, stage, h, c1, c2);
-    } else {
-        if (sw) pic_stage_kernel<true, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2);
-        else pic_stage_kernel<false, false><<<grid, block, 0, s->stream>>>(s->d, stage, h, c1, c2);
+        if (sw) return launch_pdl(s, pic_stage_kernel<true, true>, grid, block, s->smem, s->d, stage, h, c1, c2);
+        return launch_pdl(s, pic_stage_kernel<false, true>, grid, block, s->smem, s->d, stage, h, c1, c2);
     }
-    s->launches++;
-    return cudaGetLastError();
+    if (sw) return launch_pdl(s, pic_stage_kernel<true, false>, grid, block, 0, s->d, stage, h, c1, c2);
+    return launch_pdl(s, pic_stage_kernel<false, false>, grid, block, 0, s->d, stage, h, c1, c2);
 }
 
 cudaError_t launch_field(emme_pic* s, int mode, int record) {
-    pic_field_kernel<<<(s->d.nf + 31) / 32, dim3(32, PIC_FIELD_CHUNKS), 0, s->stream>>>(s->d, mode, record);
-    s->launches++;
-    return cudaGetLastError();
+    return launch_pdl(s, pic_field_kernel, dim3((s->d.nf + 31) / 32), dim3(32, PIC_FIELD_CHUNKS), 0, s->d, mode, record);
 }
 
 }  // namespace
@@ -648,6 +668,8 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     d.nparts = d.use_smem ? s->grid : 0;
     CU(dev_alloc(&d.part, (size_t)d.nparts * nf, s->stream));
     if (const char* e = std::getenv("EMME_PIC_GRAPH")) s->use_graph = std::atoi(e);
+    if (const char* e = std::getenv("EMME_PIC_PDL")) s->use_pdl = std::atoi(e);
+    if (shard_count > 1) s->use_pdl = 0;   // an NCCL kernel sits between the stage and field kernels
 
     const int ig = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
     if (sw) pic_init_kernel<true><<<ig, 256, 0, s->stream>>>(d);
