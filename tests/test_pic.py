@@ -179,3 +179,44 @@ def test_integrator_template_matches_reference(tmp_path):
     r = subprocess.run([str(exe), str(cases.GOLD / "oscillator_rk3.bin")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "fixed: 1000 steps, mismatches 0" in r.stdout and "adaptive: 400 steps (reference 400), mismatches 0" in r.stdout
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_stage_kernel_algebra_random_parameters(seed, emul, native_lib):
+    """The same replay against the ORACLE for parameters no fixture holds: random shear, k_rho,
+    tau, eta_i, drift frequency, water-bag weights, pull-back switch, cell and marker counts
+    (ragged), time step of either sign."""
+    rng = np.random.default_rng(100 + seed)
+    p = capi.EmmePicParams()
+    p.q, p.R, p.vt = rng.uniform(1.0, 3.0), rng.uniform(0.8, 1.5), rng.uniform(0.7, 1.4)
+    p.tau, p.shat = rng.uniform(0.5, 2.0), rng.uniform(-1.0, 1.5)
+    p.b_theta, p.length = rng.uniform(0.01, 0.6), rng.uniform(6.0, 25.0)
+    p.eta_i = rng.uniform(0.5, 4.0)
+    p.omega_s_i = -rng.uniform(0.2, 1.5)
+    p.omega_d_bar = rng.uniform(-1.5, 1.5)
+    p.water_bag_weight_vpara, p.water_bag_weight_vperp = rng.choice([1.0, 0.6, 1.4]), rng.choice([1.0, 0.8, 1.7])
+    p.npoints = int(rng.choice([5, 16, 33, 128]))
+    p.drift_center_transformation_switch = int(seed % 2)
+    n = int(rng.integers(1, 40)) * p.npoints + int(rng.integers(0, 7))
+    eta, v_para, v_perp, w = pic.load_markers(p, n, seed=seed)
+    w = w * (1 + 0.5j)
+    dt = float(rng.choice([0.25, 0.05, -0.1]))
+    steps = 3
+    o = O.PicOracle(p.as_dict(), eta, v_para, v_perp, w)
+    _, _, pw, coef = o.extras()
+    F = np.empty((steps, p.npoints), dtype=np.complex128)
+    e_out, w_out = np.empty(n), np.empty(n, dtype=np.complex128)
+    dp = C.POINTER(C.c_double)
+    wt = np.ascontiguousarray(w)
+    assert emul.emul_pic_run(C.byref(p), n, eta.ctypes.data_as(dp), v_para.ctypes.data_as(dp),
+                             v_perp.ctypes.data_as(dp), wt.view(np.float64).ctypes.data_as(dp),
+                             pw.ctypes.data_as(dp), coef.ctypes.data_as(dp), dt, steps,
+                             F.view(np.float64).ctypes.data_as(dp), e_out.ctypes.data_as(dp),
+                             w_out.view(np.float64).ctypes.data_as(dp)) == 0
+    for t in range(steps):
+        o.step(dt)
+        ref = o.field()
+        assert np.abs(F[t] - ref).max() <= 1e-12 * np.abs(ref).max(), (t, p.as_dict())
+    oe, ow = o.markers()
+    assert np.array_equal(e_out, oe)
+    assert np.abs(w_out - ow).max() <= 1e-12 * np.abs(ow).max()

@@ -112,6 +112,42 @@ def test_against_oracle_seeded_1k_cells(native_lib):
     s.close()
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_parameters_against_oracle(seed, native_lib):
+    """Parameters no fixture holds (random shear, k_rho, tau, eta_i, drift frequency, water-bag
+    weights, pull-back switch, ragged cell and marker counts, time step of either sign): three
+    steps on the device beside the C restatement."""
+    from emme_b200 import capi
+    rng = np.random.default_rng(100 + seed)
+    p = capi.EmmePicParams()
+    p.q, p.R, p.vt = rng.uniform(1.0, 3.0), rng.uniform(0.8, 1.5), rng.uniform(0.7, 1.4)
+    p.tau, p.shat = rng.uniform(0.5, 2.0), rng.uniform(-1.0, 1.5)
+    p.b_theta, p.length = rng.uniform(0.01, 0.6), rng.uniform(6.0, 25.0)
+    p.eta_i = rng.uniform(0.5, 4.0)
+    p.omega_s_i = -rng.uniform(0.2, 1.5)
+    p.omega_d_bar = rng.uniform(-1.5, 1.5)
+    p.water_bag_weight_vpara, p.water_bag_weight_vperp = rng.choice([1.0, 0.6, 1.4]), rng.choice([1.0, 0.8, 1.7])
+    p.npoints = int(rng.choice([5, 16, 33, 128]))
+    p.drift_center_transformation_switch = int(seed % 2)
+    n = int(rng.integers(1, 40)) * p.npoints + int(rng.integers(0, 7))
+    eta, v_para, v_perp, w = pic.load_markers(p, n, seed=seed)
+    w = w * (1 + 0.5j)
+    dt = float(rng.choice([0.25, 0.05, -0.1]))
+    s = pic.PIC_State.from_markers(p, eta, v_para, v_perp, w)
+    o = O.PicOracle(p.as_dict(), eta, v_para, v_perp, w)
+    _, _, pw, coef = s.extras()
+    assert np.array_equal(pw, o.extras()[2]) and np.array_equal(coef, o.extras()[3])
+    for t in range(3):
+        s.step(dt)
+        o.step(dt)
+        ref = o.field()
+        assert np.abs(s.current_field() - ref).max() <= FIELD_TOL * np.abs(ref).max(), (t, p.as_dict())
+    e, wg = s.markers()
+    oe, ow = o.markers()
+    assert np.array_equal(e, oe) and np.abs(wg - ow).max() <= FIELD_TOL * np.abs(ow).max()
+    s.close()
+
+
 def test_global_cells_path_matches_shared(native_lib):
     """More cells than fit in shared memory (> 6400) take the global-atomics kernel: same result
     as the oracle."""
