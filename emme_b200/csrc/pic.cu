@@ -341,7 +341,7 @@ struct emme_pic {
     int use_graph = 1;
     int use_pdl = 1;          // programmatic dependent launch between the kernels of a step
     // one cooperative launch per emme_pic_step call (grid.sync instead of kernel boundaries):
-    // measured slower than the graph (40.2 vs 38.9 us/stage at 1M markers, 21.3 vs 14.3 at 64K), kept
+    // measured slower than the graph (40.2 vs 38.9 us/stage at 1M markers, 21.3 vs 10.2 at 64K), kept
     // as a tested alternative behind EMME_PIC_PERSISTENT=1
     int use_persistent = 0;
     int pgrid = 0;
