@@ -334,6 +334,7 @@ struct emme_pic {
     long hist_cap = 0;
     long steps_done = 0;
     int shard_count = 1;
+    int next_call = 0;        // sharded protocol: 2*stage = begin(stage) expected, 2*stage+1 = finish(stage)
     int grid = 0;
     size_t smem = 0;
     cudaGraphExec_t graph = nullptr;
@@ -773,19 +774,25 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
 int emme_pic_stage_begin(emme_pic* s, double dt, int stage) {
     if (!s) return capi_fail(-1, "null handle");
     if (stage < 0 || stage > 2) return capi_fail(-3, "stage must be 0, 1 or 2");
+    if (s->next_call != 2 * stage)
+        return capi_fail(EMME_E_STATE, "stage sequence is begin(0), finish(0), begin(1), finish(1), begin(2), finish(2)");
     CU(cudaSetDevice(s->device));
     if (stage == 0)
         if (int rc = ensure_history(s, s->steps_done + 1)) return rc;
     CU(launch_stage(s, dt, stage));
     if (s->d.use_smem) CU(launch_field(s, 1, 0));   // dens = sum of this rank's partials
+    s->next_call = 2 * stage + 1;
     return 0;
 }
 
 int emme_pic_stage_finish(emme_pic* s, int stage) {
     if (!s) return capi_fail(-1, "null handle");
     if (stage < 0 || stage > 2) return capi_fail(-2, "stage must be 0, 1 or 2");
+    if (s->next_call != 2 * stage + 1)
+        return capi_fail(EMME_E_STATE, "emme_pic_stage_finish without the matching emme_pic_stage_begin");
     CU(cudaSetDevice(s->device));
     CU(launch_field(s, 2, stage == 2));
+    s->next_call = stage == 2 ? 0 : 2 * stage + 2;
     if (stage == 2) s->steps_done++;
     return 0;
 }

@@ -91,6 +91,33 @@ def test_edge_cases(native_lib):
         pic.PIC_State.from_markers(bad, g["eta"], g["v_para"], g["v_perp"], g["weight"])
 
 
+def test_stage_protocol_single_rank(native_lib):
+    """The multi-GPU entry points on one rank (no exchange needed: the density is already the
+    sum): begin/finish per stage equals emme_pic_step; a wrong sequence is EMME_E_STATE."""
+    from emme_b200 import EmmeError, capi
+    g, p, _, dt = load_case("n32")
+    m = (g["eta"], g["v_para"], g["v_perp"], g["weight"])
+    a = pic.PIC_State.from_markers(p, *m)
+    b = pic.PIC_State.from_markers(p, *m)
+    a.step(dt, 2)
+    with pytest.raises(EmmeError) as e:
+        b.stage_finish(0)
+    assert e.value.code == capi.E_STATE
+    for _ in range(2):
+        for st in range(3):
+            b.stage_begin(dt, st)
+            if st == 1:
+                with pytest.raises(EmmeError):
+                    b.stage_begin(dt, 2)
+            b.stage_finish(st)
+    assert b.steps_done() == 2
+    fa, fb = a.field_history(), b.field_history()
+    assert np.abs(fa - fb).max() <= FIELD_TOL * np.abs(fa).max()
+    assert np.array_equal(a.markers()[0], b.markers()[0])
+    a.close()
+    b.close()
+
+
 def test_against_oracle_seeded_1k_cells(native_lib):
     """A case no fixture holds: 128 cells x 64 markers, markers drawn by the product's own loader,
     the C restatement stepped beside the GPU."""
