@@ -34,7 +34,7 @@
 //   pic_driver oscillator <out.bin>
 //       the reference's Integrator template on the harmonic oscillator x'' = -x of
 //       test/test_integrator.cpp (that test no longer compiles against the current header: its
-//       state lacks initial_velocity_storage(); the state below adds exactly that).  out.bin:
+//       state lacks initial_velocity_storage()), with a state type written for this driver.  out.bin:
 //       u64 n_fixed, then (t, x0, x1) per fixed step dt = 0.01 up to t = 10; u64 n_adaptive, then
 //       (dt, t, x0, x1) per step_adaptive call with bounds 1e-5 / 1e-7 until t >= 10.
 #include <chrono>
@@ -78,57 +78,57 @@ struct emme_fixed_seed_device {
 using cplx = std::complex<double>;
 using State = PIC_State<double>;
 
-// test/test_integrator.cpp's double_state with the one member the current Integrator needs
-struct double_state {
+// Harmonic oscillator x'' = -x as a state type for the reference's Integrator template (the
+// problem of the reference's test/test_integrator.cpp, written here against the interface the
+// CURRENT template needs, include/solver_pic.h:414-456: initial_velocity_storage, put_velocity,
+// update, get_update_err, scalar * velocity, velocity + velocity).
+struct Oscillator {
     using value_type = double;
     struct velocity_type {
-        value_type v0, v1;
+        double dpos, dvel;
+        friend velocity_type operator*(double a, const velocity_type& v) { return {a * v.dpos, a * v.dvel}; }
+        friend velocity_type operator+(const velocity_type& l, const velocity_type& r) {
+            return {l.dpos + r.dpos, l.dvel + r.dvel};
+        }
     };
-    friend auto operator*(value_type a, velocity_type v) { return velocity_type{a * v.v0, a * v.v1}; }
-    friend auto operator+(velocity_type lhs, velocity_type rhs) {
-        return velocity_type{lhs.v0 + rhs.v0, lhs.v1 + rhs.v1};
+    double time = 0, pos = 0, vel = 1;
+
+    velocity_type initial_velocity_storage() const { return {0, 0}; }
+    void put_velocity(velocity_type& k) const { k = {vel, -pos}; }
+    void update(const velocity_type& k, double h) {
+        pos += k.dpos * h;
+        vel += k.dvel * h;
+        time += h;
     }
-    velocity_type initial_velocity_storage() const { return velocity_type{}; }
-    void put_velocity(velocity_type& v) {
-        v.v0 = x1;
-        v.v1 = -x0;
+    // rms of the increment relative to the rms of the state (absolute when the state vanishes)
+    double get_update_err(const velocity_type& k, double h) const {
+        const double inc = std::sqrt(.5 * (k.dpos * h * (k.dpos * h) + k.dvel * h * (k.dvel * h)));
+        const double mag = std::sqrt(.5 * (pos * pos + vel * vel));
+        return mag < std::numeric_limits<double>::epsilon() ? inc : inc / mag;
     }
-    void update(velocity_type v, value_type dt) {
-        x0 += v.v0 * dt;
-        x1 += v.v1 * dt;
-        t += dt;
-    }
-    auto get_update_err(velocity_type v, value_type dt) {
-        auto l2 = [](value_type a, value_type b) { return std::sqrt(.5 * (a * a + b * b)); };
-        return l2(x0, x1) < std::numeric_limits<value_type>::epsilon() ? l2(v.v0 * dt, v.v1 * dt)
-                                                                        : l2(v.v0 * dt, v.v1 * dt) / l2(x0, x1);
-    }
-    double t;
-    double x0, x1;
 };
 
 static int run_oscillator(const char* path) {
     std::ofstream f(path, std::ios::binary);
-    constexpr double total_t = 10;
-    {
-        double_state x2{0, 0, 1};
-        Integrator<double_state> f2(x2, 1.e-5, 1.e-7);
-        constexpr double dt = 0.01;
-        const std::uint64_t n = static_cast<std::uint64_t>(total_t / dt);
+    const double t_end = 10, h = 0.01;
+    {   // fixed step
+        Oscillator osc;
+        Integrator<Oscillator> rk(osc, 1.e-5, 1.e-7);
+        const std::uint64_t n = 1000;
         f.write(reinterpret_cast<const char*>(&n), 8);
-        for (std::size_t i = 0; i < total_t / dt; ++i) {
-            f2.step(dt);
-            const double rec[3] = {x2.t, x2.x0, x2.x1};
+        for (std::uint64_t i = 0; i < n; ++i) {
+            rk.step(h);
+            const double rec[3] = {osc.time, osc.pos, osc.vel};
             f.write(reinterpret_cast<const char*>(rec), sizeof(rec));
         }
     }
-    {
-        double_state x2{0, 0, 1};
-        Integrator<double_state> f2(x2, 1.e-5, 1.e-7);
+    {   // error-controlled step, bounds 1e-5 / 1e-7
+        Oscillator osc;
+        Integrator<Oscillator> rk(osc, 1.e-5, 1.e-7);
         std::vector<std::array<double, 4>> recs;
-        while (x2.t < total_t) {
-            auto dt = f2.step_adaptive();
-            recs.push_back({dt, x2.t, x2.x0, x2.x1});
+        while (osc.time < t_end) {
+            const double used = rk.step_adaptive();
+            recs.push_back({used, osc.time, osc.pos, osc.vel});
         }
         const std::uint64_t n = recs.size();
         f.write(reinterpret_cast<const char*>(&n), 8);

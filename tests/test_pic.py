@@ -175,7 +175,7 @@ def test_integrator_template_matches_reference(tmp_path):
     reference's template produced for the same state (tests/golden/oscillator_rk3.bin)."""
     exe = tmp_path / "test_integrator"
     subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe),
-                    str(EMUL_DIR / "test_integrator.cpp")], check=True)
+                    str(EMUL_DIR / "rk3_oscillator.cpp")], check=True)
     r = subprocess.run([str(exe), str(cases.GOLD / "oscillator_rk3.bin")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "fixed: 1000 steps, mismatches 0" in r.stdout and "adaptive: 400 steps (reference 400), mismatches 0" in r.stdout
