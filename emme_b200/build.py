@@ -17,7 +17,7 @@ ROOT = PKG.parent
 LIB = PKG / "lib" / "libemme_b200.so"
 EXE = PKG / "bin" / "emme"
 
-CU_SOURCES = [PKG / "csrc" / n for n in ("assembly.cu", "dense.cu", "qr.cu", "pic.cu", "capi.cu")]
+CU_SOURCES = [PKG / "csrc" / n for n in ("assembly.cu", "dense.cu", "peer.cu", "qr.cu", "pic.cu", "capi.cu")]
 HOST_SOURCES = [PKG / "host" / n for n in ("json.cpp", "parameters.cpp")]
 EXE_SOURCES = [PKG / "host" / n for n in ("eigen_solver.cpp", "pic_solver.cpp", "main.cpp")]
 HEADERS = (list((PKG / "csrc").glob("*.h")) + list((PKG / "csrc").glob("*.cuh")) +

@@ -12,7 +12,8 @@ import os
 # EMME_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = Path(os.environ.get("EMME_B200_LIB", PKG / "lib" / "libemme_b200.so"))
 
-E_NO_DEVICE, E_CUDA, E_BAD_ORDER, E_STATE, E_INPUT = 1000, 1001, 1002, 1003, 1004
+E_NO_DEVICE, E_CUDA, E_BAD_ORDER, E_STATE, E_INPUT, E_NONFINITE, E_PEER = 1000, 1001, 1002, 1003, 1004, 1005, 1006
+PEER_BUFS = 6
 
 
 class EmmeParams(C.Structure):
@@ -82,6 +83,9 @@ PROTOTYPES = {
     "emme_matrix_device_ptr": (_vp, [_vp, C.c_int]),
     "emme_ipc_export": (C.c_int, [_vp, C.c_int, _vp]),
     "emme_ipc_import": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "emme_peer_attach": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "emme_shard_dense": (C.c_int, [_vp, C.c_int]),
+    "emme_peer_set_timeout": (C.c_int, [C.c_double]),
     "emme_copy_matrix": (C.c_int, [_vp, C.c_int, _vp]),
     "emme_null_space": (C.c_int, [_vp, _vp]),
     "emme_get_stats": (C.c_int, [_vp, C.POINTER(EmmeStats)]),

@@ -18,6 +18,7 @@
 #include "assembly.h"
 #include "common.h"
 #include "dense.h"
+#include "peer.h"
 #include "qr.h"
 #include "run_const.h"
 
@@ -44,6 +45,7 @@ struct emme_solver {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evd0 = nullptr, evd1 = nullptr;   // dense-step timing (created once, not per step)
     // emme_copy_matrix_async: device->host copies overlap the next iterate on their own stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_src = nullptr, ev_copy_done = nullptr;
@@ -68,11 +70,19 @@ struct emme_solver {
     bool seeded = false;
     zc w{0, 0}, dw{0, 0};
     int shard_index = 0, shard_count = 1;
-    // pair-sharded assembly with direct peer stores: the two physical matrix buffers that A and
-    // A_old alternate between, and the same two buffers of every peer (CUDA IPC mappings)
+    // Peer group (one NVSwitch box).  Buffers every rank exposes to the others (CUDA IPC mappings, or
+    // plain pointers for ranks inside one process): 0, 1 = the two physical matrix buffers that A and
+    // A_old alternate between (pair-sharded assembly stores straight into them), 2 = flag page
+    // (peer.h), 3 = W, 4 = Y, 5 = partial-trace workspace (column-sharded dense step).
     void* phys[2] = {nullptr, nullptr};
-    void* peer_phys[2][EMME_MAX_PEERS] = {};
-    int peer_count = 0;               // 0: local stores only
+    unsigned long long* flag_page = nullptr;
+    void* peer_buf[EMME_PEER_BUFS][EMME_MAX_PEERS] = {};
+    bool peer_ipc[EMME_PEER_BUFS][EMME_MAX_PEERS] = {};
+    int peer_count = 0;               // 0: local stores only; > 1 once every mapping is present
+    int peer_pending = 0;             // group size announced by emme_ipc_import / emme_peer_attach
+    unsigned long long peer_epoch = 0;    // barriers passed (all ranks call them in the same order)
+    unsigned long long dense_serial = 0;  // sharded dense steps started
+    int dense_sharded = 0;
     emme_stats stats{};
     unsigned long long launches = 0;
     int refill_min = 32;
@@ -144,9 +154,11 @@ int emme_set_params(emme_solver* s, const emme_params* p) {
 int emme_destroy(emme_solver* s) {
     if (!s) return 0;
     cudaSetDevice(s->device);
-    for (int w = 0; w < 2; ++w)
+    cudaDeviceSynchronize();          // no peer may be mid-store into buffers that are about to go
+    for (int w = 0; w < EMME_PEER_BUFS; ++w)
         for (int r = 0; r < EMME_MAX_PEERS; ++r)
-            if (s->peer_phys[w][r] && s->peer_phys[w][r] != s->phys[w]) cudaIpcCloseMemHandle(s->peer_phys[w][r]);
+            if (s->peer_buf[w][r] && s->peer_ipc[w][r]) cudaIpcCloseMemHandle(s->peer_buf[w][r]);
+    cudaFree(s->flag_page);
     cudaFree(s->d_eta);
     cudaFree(s->d_g);
     cudaFree(s->d_bi);
@@ -172,6 +184,8 @@ int emme_destroy(emme_solver* s) {
     if (s->qr_graph) cudaGraphExecDestroy(s->qr_graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->evd0) cudaEventDestroy(s->evd0);
+    if (s->evd1) cudaEventDestroy(s->evd1);
     if (s->ev_copy_src) cudaEventDestroy(s->ev_copy_src);
     if (s->ev_copy_done) cudaEventDestroy(s->ev_copy_done);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -203,6 +217,8 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
+    CU(cudaEventCreate(&s->evd0));
+    CU(cudaEventCreate(&s->evd1));
     const size_t tb = sizeof(double) * npoints;
     CU(cudaMalloc(&s->d_eta, tb));
     CU(cudaMalloc(&s->d_g, tb));
@@ -254,15 +270,50 @@ static int ensure_newton_buffers(emme_solver* s) {
 }
 
 // enqueue one assembly of A(w) into `dst` (device), this handle's shard only
-static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, int shard_count) {
+static emme::PeerFlags peer_flags(const emme_solver* s) {
+    emme::PeerFlags f{};
+    f.n = s->peer_count;
+    f.me = s->shard_index;
+    for (int r = 0; r < s->peer_count; ++r) f.p[r] = (unsigned long long*)s->peer_buf[EMME_PEER_BUF_FLAGS][r];
+    return f;
+}
+
+// stream-ordered barrier over the peer group (a kernel: no host round trip, no NCCL)
+static int peer_barrier(emme_solver* s) {
+    if (s->peer_count <= 1) return 0;
+    CU(emme::launch_peer_barrier(peer_flags(s), ++s->peer_epoch, s->stream));
+    ++s->launches;
+    return 0;
+}
+
+// after a stream synchronisation: did a wait on the flag page give up?
+static int peer_check(emme_solver* s) {
+    if (s->peer_count <= 1 || !s->flag_page) return 0;
+    unsigned long long err = 0;
+    CU(cudaMemcpyAsync(&err, s->flag_page + emme::PEER_W_ERROR, sizeof err, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (err != 0) {
+        CU(cudaMemsetAsync(s->flag_page + emme::PEER_W_ERROR, 0, sizeof err, s->stream));
+        return fail(EMME_E_PEER, "multi-GPU exchange: a peer did not arrive in time (flag word " +
+                                     std::to_string(err - 1) + "); the ranks are out of step");
+    }
+    return 0;
+}
+
+// to_peers: store the entries into the matrix of EVERY rank (pair-sharded Newton path only; the
+// caller brackets the launch with peer barriers)
+static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, int shard_count,
+                            bool to_peers = false) {
+    if (!std::isfinite(w.real()) || !std::isfinite(w.imag()))
+        return fail(EMME_E_NONFINITE, "matrixAssembler: omega is not finite");
     RunConst rc = emme::make_run_const(s->p, s->N, w.real(), w.imag());
     emme::PeerSet ps{};
     ps.n = 1;
     ps.p[0] = (double2*)dst;
-    if (s->peer_count > 1 && (dst == s->phys[0] || dst == s->phys[1])) {
+    if (to_peers && s->peer_count > 1 && (dst == s->phys[0] || dst == s->phys[1])) {
         const int which = dst == s->phys[0] ? 0 : 1;
         ps.n = s->peer_count;
-        for (int r = 0; r < s->peer_count; ++r) ps.p[r] = (double2*)s->peer_phys[which][r];
+        for (int r = 0; r < s->peer_count; ++r) ps.p[r] = (double2*)s->peer_buf[which][r];
     }
     if (s->copy_pending) {
         // an asynchronous download may still be reading the buffer this assembly overwrites
@@ -362,11 +413,9 @@ static int replay_graph(emme_solver* s, cudaGraphExec_t* exec, unsigned long lon
 
 template <class RestoreRhs>
 static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    const cudaEvent_t e0 = s->evd0, e1 = s->evd1;
     CU(cudaEventRecord(e0, s->stream));
-    double tr[2];
+    double tr[2] = {0., 0.};
     int info = 0, flag = 0;
     bool rhs_intact = true;
     int path = (s->use_sym && s->Y) ? 0 : (s->optimistic ? 1 : 2);
@@ -375,11 +424,28 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
         if (path == 0) {
             CU(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
             CU(emme::launch_sym_copy_check(s->A, s->W, s->dim, s->d_flag, s->stream, &s->launches));
-            int rc = replay_graph(s, &s->sym_graph, &s->sym_graph_launches, [&](unsigned long long* nl) {
-                return emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace,
-                                              s->d_info, s->d_flag, s->stream, nl);
-            });
-            if (rc) return rc;
+            if (s->dense_sharded && s->peer_count > 1) {
+                // column-block-cyclic over the ranks: panels travel by peer stores + flags
+                emme::DensePeers dp{};
+                dp.flags = peer_flags(s);
+                dp.n = s->peer_count;
+                dp.me = s->shard_index;
+                for (int r = 0; r < s->peer_count; ++r) {
+                    dp.W[r] = s->peer_buf[EMME_PEER_BUF_W][r];
+                    dp.Y[r] = s->peer_buf[EMME_PEER_BUF_Y][r];
+                    dp.ws[r] = s->peer_buf[EMME_PEER_BUF_WS][r];
+                }
+                dp.serial = ++s->dense_serial;
+                dp.epoch = &s->peer_epoch;
+                CU(emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace, s->d_info,
+                                          s->d_flag, s->stream, &s->launches, &dp));
+            } else {
+                int rc = replay_graph(s, &s->sym_graph, &s->sym_graph_launches, [&](unsigned long long* nl) {
+                    return emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace,
+                                                  s->d_info, s->d_flag, s->stream, nl);
+                });
+                if (rc) return rc;
+            }
         } else {
             if (!rhs_intact) {
                 int rc = restore_rhs();
@@ -405,9 +471,13 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
         if (path < 2) CU(cudaMemcpyAsync(&flag, s->d_flag, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         if (path == 0) {
+            if (s->dense_sharded && s->peer_count > 1) {
+                int rc = peer_check(s);
+                if (rc) return rc;
+            }
             if (flag == 0) {
                 ++s->sym_steps;
-                s->stats.dense_flops = 4.0 * d3;
+                s->stats.dense_flops = 4.0 * d3 / ((s->dense_sharded && s->peer_count > 1) ? s->peer_count : 1);
                 break;
             }
             if ((flag & 1) || !s->optimistic) {
@@ -428,8 +498,6 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     s->stats.dense_ms = ms;
     // d_eigen_value = -1.0 / trace   (include/solver.h:139)
     *delta = -1.0 / zc(tr[0], tr[1]);
@@ -439,6 +507,18 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
                       "Linear solve failed. The factorization has been completed, but the pivot "
                       "is exactly singular at %d, so the solution could not be computed.", info);
         return fail(info, buf);
+    }
+    // The reference divides by the trace unchecked (include/solver.h:139): iterating past
+    // convergence makes A == A_old, A' = 0, trace = 0 and omega non-finite, after which its next
+    // zsysv fails or returns garbage.  Here a zero or non-finite trace is reported as a failed
+    // linear solve right away, and no assembly is ever launched at a non-finite omega.
+    if ((tr[0] == 0.0 && tr[1] == 0.0) || !std::isfinite(tr[0]) || !std::isfinite(tr[1]) ||
+        !std::isfinite(delta->real()) || !std::isfinite(delta->imag())) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf,
+                      "Linear solve failed. trace(A^-1 A') = (%g, %g): the Newton step -1/trace is not "
+                      "finite (iterating past convergence, or a non-finite matrix).", tr[0], tr[1]);
+        return fail(EMME_E_NONFINITE, buf);
     }
     return 0;
 }
@@ -466,26 +546,79 @@ int emme_shard_config(emme_solver* s, int shard_index, int shard_count) {
 static int assemble_current(emme_solver* s) {
     // with peer stores every rank writes every entry of every GPU's matrix: nothing to zero or sum
     if (s->shard_count > 1 && s->peer_count <= 1) CU(cudaMemsetAsync(s->A, 0, s->bytes(), s->stream));
-    int rc = enqueue_assembly(s, s->w, s->A, s->shard_index, s->shard_count);
+    const bool p2p = s->shard_count > 1 && s->peer_count > 1;
+    if (p2p) {
+        // The buffer about to be overwritten on EVERY rank is the one each of them may still be
+        // reading as eigen_matrix_old (secant of the previous iterate, restore_rhs of a fallback dense
+        // step, a pending download): nobody stores before everybody has arrived here.
+        if (s->copy_pending) {
+            CU(cudaStreamWaitEvent(s->stream, s->ev_copy_done, 0));
+            s->copy_pending = false;
+        }
+        int rc = peer_barrier(s);
+        if (rc) return rc;
+    }
+    int rc = enqueue_assembly(s, s->w, s->A, s->shard_index, s->shard_count, p2p);
     if (rc) return rc;
-    return collect_stats(s);
+    if (p2p) {
+        // ... and nobody reads the matrix before everybody's stores have landed
+        rc = peer_barrier(s);
+        if (rc) return rc;
+    }
+    rc = collect_stats(s);
+    if (rc) return rc;
+    return p2p ? peer_check(s) : 0;
 }
 
-// ---- peer-store plumbing (CUDA IPC): see emme_b200/parallel.py::ShardedEigenSolver ----
-int emme_ipc_export(emme_solver* s, int which, void* handle64) {
-    if (!s) return fail(-1, "null handle");
-    if (which < 0 || which > 1) return fail(-2, "emme_ipc_export: which must be 0 or 1");
-    if (!handle64) return fail(-3, "null output");
-    CU(cudaSetDevice(s->device));
+// ---- peer group plumbing: see emme_b200/parallel.py::ShardedEigenSolver ----
+static int ensure_peer_buffers(emme_solver* s) {
     int rc = ensure_newton_buffers(s);
     if (rc) return rc;
     if (!s->phys[0]) {
         s->phys[0] = s->A;
         s->phys[1] = s->Aold;
     }
+    if (!s->flag_page) {
+        CU(cudaMalloc(&s->flag_page, sizeof(unsigned long long) * emme::PEER_PAGE_WORDS));
+        CU(cudaMemset(s->flag_page, 0, sizeof(unsigned long long) * emme::PEER_PAGE_WORDS));
+    }
+    return 0;
+}
+
+static void* local_peer_buf(emme_solver* s, int which) {
+    switch (which) {
+        case EMME_PEER_BUF_MATRIX0: return s->phys[0];
+        case EMME_PEER_BUF_MATRIX1: return s->phys[1];
+        case EMME_PEER_BUF_FLAGS: return s->flag_page;
+        case EMME_PEER_BUF_W: return s->W;
+        case EMME_PEER_BUF_Y: return s->Y;
+        case EMME_PEER_BUF_WS: return s->d_sym_ws;
+    }
+    return nullptr;
+}
+
+static void peer_mapping_added(emme_solver* s, int peer_count) {
+    s->peer_pending = peer_count;
+    bool all = true;
+    for (int w = 0; w < EMME_PEER_BUFS; ++w) {
+        if (!local_peer_buf(s, w)) continue;      // W / Y / workspace only exist on the symmetric path
+        for (int r = 0; r < peer_count; ++r) all = all && s->peer_buf[w][r] != nullptr;
+    }
+    if (all) s->peer_count = peer_count;   // switch on once every mapping is present
+}
+
+int emme_ipc_export(emme_solver* s, int which, void* handle64) {
+    if (!s) return fail(-1, "null handle");
+    if (which < 0 || which >= EMME_PEER_BUFS) return fail(-2, "emme_ipc_export: which must be 0..5");
+    if (!handle64) return fail(-3, "null output");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_peer_buffers(s);
+    if (rc) return rc;
+    void* buf = local_peer_buf(s, which);
+    if (!buf) return fail(EMME_E_STATE, "emme_ipc_export: this buffer does not exist on this handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, s->phys[which]));
+    CU(cudaIpcGetMemHandle(&h, buf));
     std::memcpy(handle64, &h, 64);
     return 0;
 }
@@ -494,23 +627,65 @@ int emme_ipc_import(emme_solver* s, int peer_rank, int peer_count, int which, co
     if (!s) return fail(-1, "null handle");
     if (peer_count < 1 || peer_count > EMME_MAX_PEERS) return fail(-3, "emme_ipc_import: 1..8 peers");
     if (peer_rank < 0 || peer_rank >= peer_count) return fail(-2, "emme_ipc_import: bad peer rank");
-    if (which < 0 || which > 1) return fail(-4, "emme_ipc_import: which must be 0 or 1");
+    if (which < 0 || which >= EMME_PEER_BUFS) return fail(-4, "emme_ipc_import: which must be 0..5");
     CU(cudaSetDevice(s->device));
     if (!s->phys[0]) return fail(EMME_E_STATE, "emme_ipc_import before emme_ipc_export");
     if (peer_rank == s->shard_index) {
-        s->peer_phys[which][peer_rank] = s->phys[which];
+        s->peer_buf[which][peer_rank] = local_peer_buf(s, which);
     } else {
         if (!handle64) return fail(-5, "null handle bytes");
         cudaIpcMemHandle_t h;
         std::memcpy(&h, handle64, 64);
         void* ptr = nullptr;
         CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-        s->peer_phys[which][peer_rank] = ptr;
+        s->peer_buf[which][peer_rank] = ptr;
+        s->peer_ipc[which][peer_rank] = true;
     }
-    bool all = true;
-    for (int w = 0; w < 2; ++w)
-        for (int r = 0; r < peer_count; ++r) all = all && s->peer_phys[w][r] != nullptr;
-    if (all) s->peer_count = peer_count;   // switch on once every mapping is present
+    peer_mapping_added(s, peer_count);
+    return 0;
+}
+
+int emme_peer_attach(emme_solver* s, int peer_rank, int peer_count, emme_solver* peer) {
+    if (!s) return fail(-1, "null handle");
+    if (peer_count < 1 || peer_count > EMME_MAX_PEERS) return fail(-3, "emme_peer_attach: 1..8 peers");
+    if (peer_rank < 0 || peer_rank >= peer_count) return fail(-2, "emme_peer_attach: bad peer rank");
+    if (!peer) return fail(-4, "emme_peer_attach: null peer");
+    if (peer->dim != s->dim) return fail(-4, "emme_peer_attach: peers must have the same dimension");
+    CU(cudaSetDevice(peer->device));
+    int rc = ensure_peer_buffers(peer);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    rc = ensure_peer_buffers(s);
+    if (rc) return rc;
+    if (peer->device != s->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, s->device, peer->device));
+        if (!can) return fail(EMME_E_PEER, "emme_peer_attach: no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+    }
+    for (int w = 0; w < EMME_PEER_BUFS; ++w) s->peer_buf[w][peer_rank] = local_peer_buf(peer, w);
+    peer_mapping_added(s, peer_count);
+    return 0;
+}
+
+int emme_shard_dense(emme_solver* s, int enable) {
+    if (!s) return fail(-1, "null handle");
+    if (enable) {
+        if (s->peer_count <= 1) return fail(EMME_E_STATE, "emme_shard_dense: map the peers first");
+        if (!s->use_sym || !s->Y) return fail(EMME_E_STATE, "emme_shard_dense: the symmetric path is switched off");
+        const int nbo = emme::dense_sym_outer_block(s->dim);
+        if (nbo < 64 || nbo % 64 != 0)
+            return fail(EMME_E_STATE, "emme_shard_dense: outer block " + std::to_string(nbo) +
+                                          " (single level below dim 2049): set EMME_DENSE_NBO to a multiple of 64");
+    }
+    s->dense_sharded = enable ? 1 : 0;
+    return 0;
+}
+
+int emme_peer_set_timeout(double seconds) {
+    emme::peer_set_timeout(seconds);
     return 0;
 }
 
@@ -556,7 +731,7 @@ int emme_step_begin(emme_solver* s) {
     if (!s) return fail(-1, "null handle");
     if (!s->seeded) return fail(EMME_E_STATE, "emme_newton_trace_step before emme_seed");
     CU(cudaSetDevice(s->device));
-    zc delta;
+    zc delta(std::nan(""), std::nan(""));
     const zc dw_prev = s->dw;
     int rc = dense_delta(s, &delta, [&]() -> int {   // include/solver.h:130-139
         // A' = (A - A_old)/delta_prev is rebuilt from the intact A and A_old
@@ -565,8 +740,11 @@ int emme_step_begin(emme_solver* s) {
         ++s->launches;
         return 0;
     });
-    s->dw = delta;
-    s->w += delta;  // :140 (the reference updates omega before it checks info)
+    // :140 -- the reference updates omega before it checks info; a CUDA failure computed no delta
+    if (rc == 0 || (rc > 0 && rc <= s->dim) || rc == EMME_E_NONFINITE) {
+        s->dw = delta;
+        s->w += delta;
+    }
     if (rc) return rc;
     std::swap(s->A, s->Aold);  // eigen_matrix_old = eigen_matrix (:114) without a copy
     return assemble_current(s);  // :157
@@ -596,9 +774,7 @@ int emme_newton_trace_step(emme_solver* s, double* wr, double* wi, double* dr, d
 static int qr_delta(emme_solver* s, zc* delta) {
     if (!s->d_qr_ws) CU(cudaMalloc(&s->d_qr_ws, emme::qr_workspace_bytes(s->dim)));
     if (!s->d_qr_out) CU(cudaMalloc(&s->d_qr_out, 2 * sizeof(double2)));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    const cudaEvent_t e0 = s->evd0, e1 = s->evd1;
     CU(cudaEventRecord(e0, s->stream));
     CU(cudaMemcpyAsync(s->W, s->A, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
     // 3*dim + 4 short launches on fixed buffers: captured once, replayed (launch bound otherwise)
@@ -616,8 +792,6 @@ static int qr_delta(emme_solver* s, zc* delta) {
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     s->stats.dense_ms = ms;
     s->stats.dense_flops = (16.0 / 3.0) * (double)s->dim * s->dim * s->dim;   // Householder QR, complex
     if (info != 0) {
@@ -627,6 +801,10 @@ static int qr_delta(emme_solver* s, zc* delta) {
                               "\xe6\x97\xa0\xe6\xb3\x95\xe6\xb1\x82\xe8\xa7\xa3 (R has a zero diagonal element: cannot solve)");
     }
     *delta = -zc(out[0], out[1]) / zc(out[2], out[3]);   // :370
+    if (!std::isfinite(delta->real()) || !std::isfinite(delta->imag()))
+        return fail(EMME_E_NONFINITE, "QR-secant step is not finite: (Q^H A' v)_n = (" + std::to_string(out[2]) +
+                                          ", " + std::to_string(out[3]) + ") (iterating past convergence, or a "
+                                          "non-finite matrix)");
     return 0;
 }
 
@@ -634,8 +812,12 @@ int emme_qr_step_begin(emme_solver* s) {
     if (!s) return fail(-1, "null handle");
     if (!s->seeded) return fail(EMME_E_STATE, "emme_newton_qr_step before emme_seed");
     CU(cudaSetDevice(s->device));
-    zc delta;
+    zc delta(std::nan(""), std::nan(""));
     int rc = qr_delta(s, &delta);
+    if (rc == EMME_E_NONFINITE) {
+        s->dw = delta;
+        s->w += delta;
+    }
     if (rc) return rc;
     s->dw = delta;
     s->w += delta;               // :371
@@ -778,7 +960,9 @@ int emme_copy_matrix(emme_solver* s, int which, void* host_out) {
 
 int emme_copy_matrix_async(emme_solver* s, int which, void* pinned_host_out) {
     if (!s) return fail(-1, "null handle");
-    if (which < 0 || which > 2) return fail(-2, "emme_copy_matrix_async: which must be 0, 1 or 2");
+    // eigen_matrix_derivative (2) is rewritten by the secant and destroyed by the LU paths without
+    // waiting for a download; only the two matrices the assemblies guard are offered here
+    if (which < 0 || which > 1) return fail(-2, "emme_copy_matrix_async: which must be 0 or 1");
     if (!pinned_host_out) return fail(-3, "null output");
     void* src = emme_matrix_device_ptr(s, which);
     if (!src) return fail(EMME_E_STATE, "matrix not allocated yet (call emme_seed first)");

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include "dense.h"
+#include "peer.h"
 
 namespace cg = cooperative_groups;
 
@@ -142,7 +143,12 @@ __device__ __forceinline__ void panel_body(Comm& comm, z_t* __restrict__ W, int 
 #pragma unroll 1
     for (int c = 0; c < jb; ++c) {
         // ---- block-local pivot candidate: max |re|+|im|, ties -> lowest position ----
-        const double myv = done ? -1.0 : fabs(a[0].x) + fabs(a[0].y);
+        // a NaN candidate compares false against everything and would leave the search without a
+        // winner (position 0x7fffffff used as an address): order it as +inf instead, so that the
+        // search is total, every position is a real row, and the NaN reaches the trace where the
+        // host reports it (include/solver.h:142-153 semantics: an error, never a fault)
+        double myv = done ? -1.0 : fabs(a[0].x) + fabs(a[0].y);
+        if (myv != myv) myv = __longlong_as_double(0x7ff0000000000000LL);
         double v = myv;
         int p = done ? 0x7fffffff : my_pos;
         int t = threadIdx.x;
@@ -195,8 +201,9 @@ __device__ __forceinline__ void panel_body(Comm& comm, z_t* __restrict__ W, int 
         }
         __syncthreads();
         const double pv = s_best.val;
-        const int ppos = s_best.pos;
         const int diag = k0 + c;
+        // defensive: a position outside the matrix can never be adopted as a row
+        const int ppos = (s_best.pos >= diag && s_best.pos < dim) ? s_best.pos : diag;
         if (comm.rank() == 0 && threadIdx.x == 0) {
             ipiv[diag] = ppos;
             if (pv == 0.0 && *info == 0) *info = diag + 1;   // exactly singular (LAPACK info > 0)
@@ -737,7 +744,7 @@ __device__ long long g_ps_clocks[8];   // scratch/panel_bench.cu: phase boundari
 #endif
 
 __global__ void __launch_bounds__(128)
-panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int k0, int jb, int ycols,
+panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int k0, int jb, int ycol0, int ycols,
                  int n_row_ctas, int tile, double tau, int* __restrict__ flag) {
     static_assert(NB == 32, "thread mapping of the diagonal-block factorisation");
     extern __shared__ __align__(16) unsigned char ps_smem_raw[];
@@ -751,7 +758,7 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
     PS_CLOCK(0);
     const bool row_role = (int)blockIdx.x < n_row_ctas;
     const int r0 = jb + (int)blockIdx.x * tile;                         // first row offset below k0
-    const int c0 = ((int)blockIdx.x - n_row_ctas) * tile;               // first column of Y
+    const int c0 = ycol0 + ((int)blockIdx.x - n_row_ctas) * tile;       // first column of Y
     const int ldy = tile + 2;
     // ---- the diagonal block first (it is needed first), then the operand tile (cp.async) ----
     const int gi = tid >> 2, gq = tid & 3;
@@ -1002,11 +1009,20 @@ transpose_invd_kernel(const z_t* __restrict__ Y, const z_t* __restrict__ W, z_t*
 
 // partial[chunk][t] = sum over tile t = (I, J), I >= J, of P_ij * (I > J ? B_ij + B_ji : B_ji) with
 // P = YT * Y = A^-1 (only k >= 64 I contributes: YT is upper, Y lower triangular).
+// Sharded dense step: a rank forms the tiles t = t_first + blockIdx.x * t_stride and stores each
+// partial at its GLOBAL slot [chunk][t] of the workspace of EVERY rank (peer stores), so that all
+// ranks reduce the same array in the same order (bitwise the single-GPU trace).
+struct PartialDst {
+    z_t* p[EMME_MAX_PEERS];
+    int n;
+};
+
 __global__ void __launch_bounds__(256, 2)
 ptrace_kernel(const z_t* __restrict__ YT, const z_t* __restrict__ Y, const z_t* __restrict__ Bd, int dim,
-              int ck, z_t* __restrict__ partial) {
+              int ck, const PartialDst partial, int ntiles, int t_first, int t_stride) {
     __shared__ double red[2][8];
-    const int t = blockIdx.x;
+    const int t = t_first + (int)blockIdx.x * t_stride;
+    if (t >= ntiles) return;
     int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
     while ((I + 1) * (I + 2) / 2 <= t) ++I;
     while (I * (I + 1) / 2 > t) --I;
@@ -1016,7 +1032,8 @@ ptrace_kernel(const z_t* __restrict__ YT, const z_t* __restrict__ Y, const z_t* 
     const int kstart = I * GM + (int)blockIdx.y * ck;
     const int kend = blockIdx.y + 1 == gridDim.y ? dim : (kstart + ck < dim ? kstart + ck : dim);
     if (kstart >= dim) {
-        if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + t] = make_double2(0., 0.);
+        if (threadIdx.x == 0)
+            for (int r = 0; r < partial.n; ++r) partial.p[r][(size_t)blockIdx.y * ntiles + t] = make_double2(0., 0.);
         return;
     }
     GemmAcc acc;
@@ -1056,7 +1073,7 @@ ptrace_kernel(const z_t* __restrict__ YT, const z_t* __restrict__ Y, const z_t* 
     if (threadIdx.x == 0) {
         double x = 0., y = 0.;
         for (int w = 0; w < 8; ++w) { x += red[0][w]; y += red[1][w]; }
-        partial[(size_t)blockIdx.y * gridDim.x + t] = make_double2(x, y);
+        for (int r = 0; r < partial.n; ++r) partial.p[r][(size_t)blockIdx.y * ntiles + t] = make_double2(x, y);
     }
 }
 
@@ -1407,6 +1424,136 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
 }
 
 
+// ------------------------------------------------------------------ symmetric path: blocked kernels
+// Two-level (outer block NBO = 256 > NB) form of the symmetric path, written so that it SHARDS over
+// the GPUs of one box by column blocks (outer block K belongs to rank K mod P, for W and for Y):
+//   * the owner factors panel K (NB-wide panels + updates inside the outer block) carrying only the
+//     DIAGONAL block of the identity, so that it ends with M_KK = (L_KK)^-1 next to the L panel and
+//     the mirrored block row U12 = D L21^T;
+//   * panel K = {L panel, U12, M_KK} is stored into the W / Y buffers of every other rank through
+//     their peer mappings and announced with a release store into their flag pages;
+//   * every rank then transforms rows K of ITS columns of Y with one GEMM (Y_K <- M_KK Y_K, final
+//     rows of M = L^-1, written straight into the Y of every rank from the epilogue) and applies the
+//     rank-NBO update to ITS column blocks of W (lower block triangle) and Y;
+//   * look-ahead: the owner of panel K+1 updates that block first, factors and publishes it, and only
+//     then does the rest of its update -- the panel factorisation leaves the critical path.
+// With P = 1 the same code is the single-GPU path; every matrix element sees the same operations in
+// the same order for every P, so the trace is bitwise independent of the number of GPUs.
+
+struct ShardPtrs {
+    z_t* W[EMME_MAX_PEERS];
+    z_t* Y[EMME_MAX_PEERS];
+    int n, me;
+};
+
+// Copy panel K to every other rank: W[K0:dim, K0:KE) (L panel, factored diagonal block included),
+// W[K0:KE, KE:dim) (U12) and Y[K0:KE, K0:KE) (M_KK).  Row-contiguous 16-byte accesses.
+__global__ void __launch_bounds__(256)
+publish_panel_kernel(const ShardPtrs sp, int ld, int dim, int K0, int JB) {
+    const int KE = K0 + JB;
+    const size_t n1 = (size_t)(dim - K0) * JB;          // L panel
+    const size_t n2 = (size_t)JB * (dim - KE);          // U12
+    const size_t n3 = (size_t)JB * JB;                  // M_KK
+    const size_t total = n1 + n2 + n3;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        size_t off;
+        bool in_y = false;
+        if (e < n1) {
+            off = (size_t)(K0 + e / JB) * ld + K0 + e % JB;
+        } else if (e < n1 + n2) {
+            const size_t f = e - n1;
+            const int w = dim - KE;
+            off = (size_t)(K0 + f / w) * ld + KE + f % w;
+        } else {
+            const size_t f = e - n1 - n2;
+            off = (size_t)(K0 + f / JB) * ld + K0 + f % JB;
+            in_y = true;
+        }
+        const z_t v = in_y ? sp.Y[sp.me][off] : sp.W[sp.me][off];
+#pragma unroll
+        for (int r = 0; r < EMME_MAX_PEERS; ++r)
+            if (r < sp.n && r != sp.me) (in_y ? sp.Y[r] : sp.W[r])[off] = v;
+    }
+}
+
+// column tile t of a block-cyclic list of outer blocks: blocks blk0, blk0+P, ... each NBO/64 tiles wide
+__device__ __forceinline__ int shard_col0(int t, int blk0, int P, int nbo) {
+    const int tpb = nbo / GN;
+    return (blk0 + (t / tpb) * P) * nbo + (t % tpb) * GN;
+}
+
+// S[0:JB, cols] = M_KK * Y[K0:KE, cols] for this rank's Y column blocks blk0, blk0+P, ... < K
+// (M_KK = Y[K0:KE, K0:KE), unit lower triangular: row tile `by` only needs k < 64 (by + 1)).
+// The result -- final rows K0..KE of M = L^-1 -- goes to the local scratch S (the B operand of the
+// update that follows; Y itself is still being read by other CTAs) and into Y of every OTHER rank.
+__global__ void __launch_bounds__(256, 2)
+ydiag_kernel(const ShardPtrs sp, z_t* __restrict__ S, int ld, int dim, int K0, int JB, int blk0, int P, int nbo) {
+    const int col0 = shard_col0(blockIdx.x, blk0, P, nbo);
+    if (col0 >= K0) return;
+    const int m0 = blockIdx.y * GM;
+    if (m0 >= JB) return;
+    const z_t* Yl = sp.Y[sp.me];
+    const int N = K0 - col0 < GN ? K0 - col0 : GN;
+    const int Kk = m0 + GM < JB ? m0 + GM : JB;
+    GemmAcc acc;
+    zgemm_mainloop(acc, Yl + (size_t)K0 * ld + K0, ld, Yl + (size_t)K0 * ld + col0, ld, JB, N, Kk, m0, 0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + acc_row(i);
+        if (m >= JB) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = acc_col(j, e);
+                if (n >= N) continue;
+                const z_t v = make_double2(acc.re[i][j][e], acc.im[i][j][e]);
+                S[(size_t)m * ld + col0 + n] = v;
+                const size_t off = (size_t)(K0 + m) * ld + col0 + n;
+#pragma unroll
+                for (int r = 0; r < EMME_MAX_PEERS; ++r)
+                    if (r < sp.n && r != sp.me) sp.Y[r][off] = v;
+            }
+        }
+    }
+}
+
+// Y[K0:KE, cols] <- S[0:JB, cols] for the same column list (the local copy of the final rows)
+__global__ void __launch_bounds__(256)
+ycopy_kernel(z_t* __restrict__ Y, const z_t* __restrict__ S, int ld, int K0, int JB, int blk0, int P, int nbo) {
+    const int col0 = shard_col0(blockIdx.x, blk0, P, nbo);
+    if (col0 >= K0) return;
+    const int c = threadIdx.x & 63;
+    if (col0 + c >= K0) return;
+    for (int m = (threadIdx.x >> 6) + 4 * blockIdx.y; m < JB; m += 4 * gridDim.y)
+        Y[(size_t)(K0 + m) * ld + col0 + c] = S[(size_t)m * ld + col0 + c];
+}
+
+// Rank-JB update with panel K of this rank's column blocks, one launch:
+//   W tiles (x < nwt): blocks wblk0, wblk0+P, ...:  W[KE:, c] -= L[KE:, K] U12[K, c], lower block triangle only
+//   Y tiles          : blocks yblk0, yblk0+P, ... <= K:  Y[KE:, c] -= L[KE:, K] S[:, c]
+__global__ void __launch_bounds__(256, 2)
+shard_update_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, const z_t* __restrict__ S, int ld, int dim, int K0,
+                    int JB, int wblk0, int nwt, int yblk0, int P, int nbo) {
+    const int KE = K0 + JB;
+    const int by = blockIdx.y;
+    const int M = dim - KE;
+    if (by * GM >= M) return;
+    const z_t* A = W + (size_t)KE * ld + K0;
+    if ((int)blockIdx.x < nwt) {
+        const int col0 = shard_col0(blockIdx.x, wblk0, P, nbo);
+        if (col0 >= dim || KE + by * GM < col0) return;          // outside / above the block diagonal
+        const int N = dim - col0 < GN ? dim - col0 : GN;
+        zgemm_sub_tile(W + (size_t)KE * ld + col0, ld, A, ld, W + (size_t)K0 * ld + col0, ld, M, N, JB, 0, by);
+    } else {
+        const int col0 = shard_col0((int)blockIdx.x - nwt, yblk0, P, nbo);
+        if (col0 >= KE) return;
+        const int N = KE - col0 < GN ? KE - col0 : GN;
+        zgemm_sub_tile(Y + (size_t)KE * ld + col0, ld, A, ld, S + col0, ld, M, N, JB, 0, by);
+    }
+}
+
 // ------------------------------------------------------------------ symmetric path: driver
 size_t dense_sym_workspace_bytes(int dim) {
     const size_t nt = (dim + GM - 1) / GM;
@@ -1424,59 +1571,174 @@ cudaError_t launch_sym_copy_check(const void* A, void* W, int dim, int* d_flag, 
     return cudaGetLastError();
 }
 
+int dense_sym_outer_block(int dim) { return g_nbo > 0 ? g_nbo : (dim <= 2048 ? NB : 256); }
+
+#define DCHK(call)                        \
+    do {                                  \
+        cudaError_t e__ = (call);         \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
 // trace(A^-1 B) for complex symmetric A, W holding A's lower block triangle (destroyed: on return
 // W holds the complete L\U factors), Y and YT dim x dim scratch, B read only.  Raises bit 1 of
 // *d_flag when partial pivoting would have interchanged rows (the caller then repeats the step with
 // the pivoting LU).  *d_flag is NOT cleared here.
+// `peers` (may be null = one GPU): the W / Y / workspace / flag-page mappings of the ranks that share
+// the step; *peers->epoch and peers->serial drive the barriers and panel flags.
 cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int dim, void* sym_workspace,
                              void* d_trace, int* d_info, int* d_flag, cudaStream_t stream,
-                             unsigned long long* n_launches) {
+                             unsigned long long* n_launches, const DensePeers* peers) {
     unsigned long long nl = 0;
     z_t* W = (z_t*)Wv;
     z_t* Y = (z_t*)Yv;
     z_t* YT = (z_t*)YTv;
     const int ld = dim;
-    cudaError_t e = gemm_setup();
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(d_info, 0, sizeof(int), stream);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(Y, 0, sizeof(z_t) * (size_t)dim * dim, stream);
-    if (e != cudaSuccess) return e;
+    const int P = peers ? peers->n : 1, me = peers ? peers->me : 0;
+    DCHK(gemm_setup());
+    DCHK(cudaMemsetAsync(d_info, 0, sizeof(int), stream));
+    DCHK(cudaMemsetAsync(Y, 0, sizeof(z_t) * (size_t)dim * dim, stream));
     set_identity_diag_kernel<<<(dim + 255) / 256, 256, 0, stream>>>(Y, dim);
     ++nl;
     // outer block: single level while the step is launch bound; 256 columns beyond (measured at
     // dim 8192: 84.0 ms with 128, 78.5 with 256, 78.8 with 512; at 2048 all within 1 %)
-    const int NBO = g_nbo > 0 ? g_nbo : (dim <= 2048 ? NB : 256);
+    int NBO = dense_sym_outer_block(dim);
+    if (P > 1 && NBO < GN) NBO = GN;           // sharding needs tile-aligned column blocks
     auto at = [&](z_t* M, int r, int c) { return M + (size_t)r * ld + c; };
-    // C1 = W[r1:, c1:c1+N1) (lower block triangle), C2 = Y[r1:r1+M2, 0:N2), A = W[r1:, kb:kb+K)
-    auto update = [&](int r1, int M1, int c1, int N1, int M2, int N2, int kb, int K) {
+    // tile = rows (columns of Y) per CTA: small systems get small tiles (more SMs share the products)
+    const int tile = dim <= 4736 ? 16 : (dim <= 9472 ? 32 : 64);
+    // C1 = W[r1:, c1:c1+N1) (lower block triangle), C2 = Y[r1:r1+M2, yc:yc+N2), A = W[r1:, kb:kb+K)
+    auto update = [&](int r1, int M1, int c1, int N1, int M2, int yc, int N2, int kb, int K) {
         const int M = M1 > M2 ? M1 : M2;
         if (M <= 0) return;
         const int nx1 = M1 > 0 ? (N1 + GN - 1) / GN : 0, nx2 = M2 > 0 ? (N2 + GN - 1) / GN : 0;
         if (nx1 + nx2 == 0) return;
         dim3 g(nx1 + nx2, (M + GM - 1) / GM);
         zgemm_sym2_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(at(W, r1, c1), at(W, kb, c1), M1, N1, nx1,
-                                                            at(Y, r1, 0), at(Y, kb, 0), M2, N2, ld,
+                                                            at(Y, r1, yc), at(Y, kb, yc), M2, N2, ld,
                                                             at(W, r1, kb), K);
         ++nl;
     };
-    for (int K0 = 0; K0 < dim; K0 += NBO) {
-        const int JB = dim - K0 < NBO ? dim - K0 : NBO;
-        const int KE = K0 + JB;
-        for (int k0 = K0; k0 < KE; k0 += NB) {
-            const int jb = KE - k0 < NB ? KE - k0 : NB;
-            const int ke = k0 + jb;
-            // tile = rows (columns of Y) per CTA: small systems get small tiles (more SMs share the products)
-            const int tile = dim <= 4736 ? 16 : (dim <= 9472 ? 32 : 64);
-            const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
-            panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, ke, n_row,
-                                                                            tile, g_tau, d_flag);
-            ++nl;
-            // inside the outer block: columns [ke, KE) of W below the panel, rows [ke, KE) of Y
-            if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, ke, k0, jb);
+    ShardPtrs sp{};
+    PartialDst pd{};
+    sp.n = P;
+    sp.me = me;
+    pd.n = P;
+    for (int r = 0; r < P; ++r) {
+        sp.W[r] = peers ? (z_t*)peers->W[r] : W;
+        sp.Y[r] = peers ? (z_t*)peers->Y[r] : Y;
+        pd.p[r] = peers ? (z_t*)peers->ws[r] : (z_t*)sym_workspace;
+    }
+    if (NBO % GN != 0 || NBO == NB) {
+        // ---- single level / unaligned outer block: one GPU only (small systems, launch bound) ----
+        if (P > 1) return cudaErrorInvalidValue;
+        for (int K0 = 0; K0 < dim; K0 += NBO) {
+            const int JB = dim - K0 < NBO ? dim - K0 : NBO;
+            const int KE = K0 + JB;
+            for (int k0 = K0; k0 < KE; k0 += NB) {
+                const int jb = KE - k0 < NB ? KE - k0 : NB;
+                const int ke = k0 + jb;
+                const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
+                panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, 0, ke, n_row,
+                                                                                tile, g_tau, d_flag);
+                ++nl;
+                // inside the outer block: columns [ke, KE) of W below the panel, rows [ke, KE) of Y
+                if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, 0, ke, k0, jb);
+            }
+            // everything below the outer block: rank-JB update
+            if (KE < dim) update(KE, dim - KE, KE, dim - KE, dim - KE, 0, KE, K0, JB);
         }
-        // everything below the outer block: rank-JB update
-        if (KE < dim) update(KE, dim - KE, KE, dim - KE, dim - KE, KE, K0, JB);
+    } else {
+        // ---- blocked, column-block-cyclic over P ranks (P = 1: the single-GPU path) ----
+        z_t* S = YT;                       // scratch rows 0..NBO of YT (YT is written at the very end)
+        const int nb = (dim + NBO - 1) / NBO;
+        if (P > 1 && nb > PEER_MAX_PANELS) return cudaErrorInvalidValue;
+        if (P > 1) {
+            // nobody stores into a peer's W / Y before that peer has initialised them
+            DCHK(launch_peer_barrier(peers->flags, ++*peers->epoch, stream));
+            ++nl;
+        }
+        auto owner = [&](int K) { return K % P; };
+        auto first_own = [&](int from) {   // smallest own block index >= from
+            int c = from + ((me - from) % P + P) % P;
+            return c;
+        };
+        auto factor_publish = [&](int K) -> cudaError_t {
+            const int K0 = K * NBO;
+            const int JB = dim - K0 < NBO ? dim - K0 : NBO;
+            const int KE = K0 + JB;
+            for (int k0 = K0; k0 < KE; k0 += NB) {
+                const int jb = KE - k0 < NB ? KE - k0 : NB;
+                const int ke = k0 + jb;
+                const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke - K0 + tile - 1) / tile;
+                panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, K0, ke, n_row,
+                                                                                tile, g_tau, d_flag);
+                ++nl;
+                if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, K0, ke - K0, k0, jb);
+            }
+            if (P > 1) {
+                const size_t total = (size_t)(dim - K0) * JB + (size_t)JB * (dim - KE) + (size_t)JB * JB;
+                int blocks = (int)((total + 1023) / 1024);
+                if (blocks > 1184) blocks = 1184;
+                publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB);
+                DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, stream));
+                nl += 2;
+            }
+            return cudaGetLastError();
+        };
+        auto shard_update = [&](int K0, int JB, int wblk0, int wblk_end, int yblk0, int yblk_end) {
+            // W blocks wblk0, wblk0+P, ... < wblk_end; Y blocks yblk0, yblk0+P, ... < yblk_end
+            const int KE = K0 + JB;
+            const int M = dim - KE;
+            if (M <= 0) return;
+            const int tpb = NBO / GN;
+            const int nwb = wblk0 < wblk_end ? (wblk_end - wblk0 + P - 1) / P : 0;
+            const int nyb = yblk0 < yblk_end ? (yblk_end - yblk0 + P - 1) / P : 0;
+            if (nwb + nyb == 0) return;
+            dim3 g((nwb + nyb) * tpb, (M + GM - 1) / GM);
+            shard_update_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(W, Y, S, ld, dim, K0, JB, wblk0, nwb * tpb, yblk0,
+                                                                  P, NBO);
+            ++nl;
+        };
+        if (owner(0) == me) DCHK(factor_publish(0));
+        for (int K = 0; K < nb; ++K) {
+            const int K0 = K * NBO;
+            const int JB = dim - K0 < NBO ? dim - K0 : NBO;
+            const int KE = K0 + JB;
+            if (owner(K) != me) {
+                DCHK(launch_peer_wait(peers->flags, PEER_W_PANEL + K, peers->serial, stream));
+                ++nl;
+            }
+            // rows K of my columns of Y become final: Y_K <- M_KK Y_K (blocks < K), via the scratch S
+            const int y0 = first_own(0);
+            if (y0 < K) {
+                const int nyb = (K - y0 + P - 1) / P;
+                dim3 g(nyb * (NBO / GN), (JB + GM - 1) / GM);
+                ydiag_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(sp, S, ld, dim, K0, JB, y0, P, NBO);
+                dim3 gc(nyb * (NBO / GN), (JB + 15) / 16 < 8 ? (JB + 15) / 16 : 8);
+                ycopy_kernel<<<gc, 256, 0, stream>>>(Y, S, ld, K0, JB, y0, P, NBO);
+                nl += 2;
+            }
+            if (owner(K) == me) {
+                // the owner's own block: S_K = M_KK (B operand of the update of Y[KE:, block K])
+                DCHK(cudaMemcpy2DAsync(S + K0, sizeof(z_t) * ld, at(Y, K0, K0), sizeof(z_t) * ld, sizeof(z_t) * JB, JB,
+                                       cudaMemcpyDeviceToDevice, stream));
+            }
+            if (KE >= dim) continue;
+            const int w0 = first_own(K + 1);
+            if (K + 1 < nb && owner(K + 1) == me) {
+                // look-ahead: bring block K+1 up to date, factor and publish it, then the rest
+                shard_update(K0, JB, K + 1, K + 2, 0, 0);
+                DCHK(factor_publish(K + 1));
+                shard_update(K0, JB, K + 1 + P, nb, y0, K + 1);
+            } else {
+                shard_update(K0, JB, w0, nb, y0, K + 1);
+            }
+        }
+        if (P > 1) {
+            // every rank's final rows of Y have arrived everywhere
+            DCHK(launch_peer_barrier(peers->flags, ++*peers->epoch, stream));
+            ++nl;
+        }
     }
     // A^-1 = M^T D^-1 M on the lower block triangle, contracted with B on the fly
     {
@@ -1490,9 +1752,18 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
         if (nchunks > (dim + 127) / 128) nchunks = (dim + 127) / 128;
         if (nchunks < 1) nchunks = 1;
         const int ck = (((dim + nchunks - 1) / nchunks) + GK - 1) / GK * GK;
-        ptrace_kernel<<<dim3(ntiles, nchunks), 256, G_SMEM_BYTES, stream>>>(YT, Y, (const z_t*)Bv, dim, ck,
-                                                                            (z_t*)sym_workspace);
-        ++nl;
+        const int my_tiles = (ntiles - me + P - 1) / P;
+        if (my_tiles > 0) {
+            ptrace_kernel<<<dim3(my_tiles, nchunks), 256, G_SMEM_BYTES, stream>>>(YT, Y, (const z_t*)Bv, dim, ck, pd,
+                                                                                  ntiles, me, P);
+            ++nl;
+        }
+        if (P > 1) {
+            // "my partials are stored everywhere" + flags; wait for everybody's, OR the flags
+            DCHK(launch_peer_post(peers->flags, peers->serial, (const double2*)d_trace, d_flag, d_info, stream));
+            DCHK(launch_peer_collect(peers->flags, peers->serial, (double2*)d_trace, d_flag, d_info, stream));
+            nl += 2;
+        }
         reduce_partials_kernel<<<1, 256, 0, stream>>>((const z_t*)sym_workspace, ntiles * nchunks,
                                                       (z_t*)d_trace);
         ++nl;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "peer.h"
+
 #define DENSE_NB 32
 
 namespace emme {
@@ -29,9 +31,24 @@ cudaError_t launch_conj_normalise(const void* X, int ld, int dim, void* rhs, int
 size_t dense_sym_workspace_bytes(int dim);
 cudaError_t launch_sym_copy_check(const void* A, void* W, int dim, int* d_flag, cudaStream_t stream,
                                   unsigned long long* n_launches);
+// Column-sharded variant: the ranks of one box share the step.  W, Y, ws are the
+// same three buffers on every rank (peer mappings, index = rank; own entry = local pointer), flags
+// the flag pages; `serial` is this dense step's number (identical on every rank, increasing), *epoch
+// the rank's barrier counter (all ranks pass the same barriers in the same order).
+struct DensePeers {
+    PeerFlags flags;
+    void* W[EMME_MAX_PEERS];
+    void* Y[EMME_MAX_PEERS];
+    void* ws[EMME_MAX_PEERS];
+    int n, me;
+    unsigned long long serial;
+    unsigned long long* epoch;
+};
 cudaError_t launch_trace_sym(void* W, void* Y, void* YT, const void* B, int dim, void* sym_workspace,
                              void* d_trace, int* d_info, int* d_flag, cudaStream_t stream,
-                             unsigned long long* n_launches);
+                             unsigned long long* n_launches, const DensePeers* peers = nullptr);
+// outer block width the symmetric path uses for this size (NB = single level)
+int dense_sym_outer_block(int dim);
 void dense_set_pivot_threshold(double tau);
 // Ad = (A - Aold)/delta over n complex entries
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,

@@ -6,15 +6,23 @@ Two ways the path shards:
 * scan-parallel (weak scaling, no data-path collective): independent scan points / omega
   starts are dealt round-robin to ranks; only (omega, iterations, status) is gathered at the end.
   `scan_partition`, `gather_results`.
-* row/pair-sharded assembly (strong scaling): the work items of ONE assembly (pairs i<j in
-  diagonal-major order, times 3 modes when electromagnetic) are dealt to ranks in chunks of 32
-  (`shard_items`).  Default (`exchange="p2p"`): the ranks map each other's matrices with CUDA IPC
-  and the assembly kernel stores every entry it computes straight into the matrix of EVERY GPU
-  over NVLink while it computes -- compute and exchange are one kernel, only a barrier follows.
-  Fallback (`exchange="allreduce"`): each rank fills its entries of a zeroed buffer and one NCCL
-  all-reduce (sum) completes the matrix; the shares are disjoint, so either way the result is
-  bit-identical to a single-GPU assembly.  The dense step is replicated on every rank (identical
-  inputs give identical delta, no broadcast needed).  `ShardedEigenSolver`.
+* one problem over N GPUs (strong scaling), `ShardedEigenSolver`:
+  - assembly: the work items of ONE assembly (pairs i<j in diagonal-major order, times 3 modes when
+    electromagnetic) are dealt to ranks in chunks of 32 (`shard_items`).  Default
+    (`exchange="p2p"`): the ranks map each other's buffers with CUDA IPC and the assembly kernel
+    stores every entry it computes straight into the matrix of EVERY GPU over NVLink while it
+    computes; two stream-ordered device barriers (release/acquire flags in peer memory, csrc/peer.cu)
+    bracket the launch: nobody overwrites a buffer a peer may still read as eigen_matrix_old, nobody
+    reads before every store has landed.  No NCCL, no host round trip.  Baseline to compare against
+    (`exchange="allreduce"`): each rank fills its entries of a zeroed buffer and one NCCL all-reduce
+    (sum) completes the matrix.  Either way the result is bit-identical to a single-GPU assembly.
+  - dense step (`shard_dense`, default from dim 4096): the symmetric L D L^T path is column-block-
+    cyclic over the ranks; the owner of a 256-column panel factors it and stores it into every
+    peer's work matrix, announces it with a flag, and everybody updates its own columns; the
+    partial traces are all-gathered by peer stores and reduced in one fixed order, so delta is
+    BITWISE the single-GPU delta and every rank holds the same omega without a broadcast.
+  `LocalShardedGroup` drives the same protocol from ONE process (one host thread per rank, several
+  ranks per device allowed): the CPU-less way to test it on a single GPU.
 * PIC method (row N4): the markers are dealt to ranks in contiguous blocks (`marker_shard`); every
   Runge-Kutta stage deposits the rank's markers and ends with ONE all-reduce (sum) of the density,
   2 * npoints doubles (16 KB at 1024 cells) -- the path's only real exchange step -- after which
@@ -87,10 +95,13 @@ def solve_scan_parallel(base_text, key, values, omega0, device=0, group=None):
         try:
             inp = Input(text=base_text)
             inp.set_number(key, v)
+            p, n = inp.params()
+            if solver is not None and (n != solver.npoints or solver.dim != (n if p.beta_e == 0.0 else 2 * n)):
+                solver.close()                      # the scanned key changed the mesh: new buffers
+                solver = None
             if solver is None:
                 solver = EigenSolver.from_input(inp, device=device)
             else:                                   # same mesh: reuse the handle and its buffers
-                p, _ = inp.params()
                 capi.check(solver._lib.emme_set_params(solver._h, p))
                 tabs = [np.ascontiguousarray(t) for t in inp.tables()]
                 capi.check(solver._lib.emme_set_tables(solver._h, *[t.ctypes.data for t in tabs]))
@@ -100,6 +111,47 @@ def solve_scan_parallel(base_text, key, values, omega0, device=0, group=None):
                        converged=abs(iters[-1][1]) < abs(inp.number("iteration_precision") * w))
         except Exception as e:                       # noqa: BLE001 - recorded, scan continues
             rec.update(eigenvalue="NaN", reason=str(e))
+        local.append((k, rec))
+    if solver is not None:
+        solver.close()
+    return gather_results(local)
+
+
+def solve_scan_texts(texts, starts, device=0, group=None):
+    """Scan-parallel driver over complete input.json texts (BASELINE config C5: one file per
+    point, each with its own start): point k goes to rank k % world, a rank reuses one handle for
+    all its points of the same mesh, records are gathered on every rank in scan order."""
+    import torch.distributed as dist
+
+    from .solver import Input, solve_once_eigen
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    local = []
+    solver = None
+    for k, txt in scan_partition(list(texts), rank, world):
+        rec = {"point": k, "rank": rank}
+        try:
+            inp = Input(text=txt)
+            p, n = inp.params()
+            if solver is not None and (n != solver.npoints or solver.dim != (n if p.beta_e == 0.0 else 2 * n)):
+                solver.close()                      # another mesh: the handle's buffers do not fit
+                solver = None
+            if solver is None:
+                solver = EigenSolver.from_input(inp, device=device)
+            else:                                   # same mesh: reuse the handle and its buffers
+                capi.check(solver._lib.emme_set_params(solver._h, p))
+                tabs = [np.ascontiguousarray(t) for t in inp.tables()]
+                capi.check(solver._lib.emme_set_tables(solver._h, *[t.ctypes.data for t in tabs]))
+                solver.synchronize()
+            w, iters, _ = solve_once_eigen(inp, starts[k], solver=solver)
+            rec.update(eigenvalue=[w.real, w.imag], iterations=len(iters),
+                       converged=bool(abs(iters[-1][1]) < abs(inp.number("iteration_precision") * w)))
+        except Exception as e:                       # noqa: BLE001 - recorded, scan continues
+            rec.update(eigenvalue="NaN", reason=str(e))
+            if solver is not None:                   # a failed point must not poison the next one
+                solver.close()
+                solver = None
         local.append((k, rec))
     if solver is not None:
         solver.close()
@@ -145,6 +197,16 @@ class ShardedPIC:
             self._stream = torch.cuda.ExternalStream(self.state.stream(), device=device)
             self._dens = torch.as_tensor(_DevVector(self.state.density_ptr(), 2 * self.nf),
                                          device=f"cuda:{device}")
+
+    @classmethod
+    def from_seed(cls, params, n_markers, seed=1, device=0, group=None):
+        """Load `n_markers` markers with the reference's mt19937 stream (PIC_State::initialize_marker)
+        and keep this rank's block."""
+        from .pic import load_markers
+        return cls(params, load_markers(params, n_markers, seed=seed), device=device, group=group)
+
+    def exchange_description(self):
+        return "one NCCL all-reduce (sum) of 2*npoints doubles per stage on the handle's stream"
 
     def step(self, dt, nsteps=1):
         import torch
@@ -193,12 +255,13 @@ def device_view(solver, which=0, device=0):
 
 
 class ShardedEigenSolver(EigenSolver):
-    """EigenSolver whose assemblies are split over the ranks of a process group.
+    """EigenSolver whose assemblies -- and, from dim 4096 up, dense steps -- are split over the
+    ranks of a process group (one process per GPU).
 
     Same public surface (seed, newtonTraceSecantIteration, eigen_value ...); every rank ends each
     call with the full matrices and the same eigen_value."""
 
-    def __init__(self, params, npoints, eta, g, bi, device=0, group=None, exchange="p2p"):
+    def __init__(self, params, npoints, eta, g, bi, device=0, group=None, exchange="p2p", shard_dense=None):
         import torch.distributed as dist
         super().__init__(params, npoints, eta, g, bi, device=device)
         self._group = group
@@ -207,39 +270,52 @@ class ShardedEigenSolver(EigenSolver):
         self.world = dist.get_world_size(group)
         self.shard_config(self.rank, self.world)
         self.exchange = exchange if self.world > 1 else "none"
+        self.dense_sharded = False
         if self.exchange == "p2p":
             self._map_peers()
+            if shard_dense is None:
+                shard_dense = self.dim >= 4096
+            if shard_dense:
+                capi.check(self._lib.emme_shard_dense(self._h, 1))
+                self.dense_sharded = True
 
     def _map_peers(self):
-        """Exchange CUDA IPC handles of the two matrix buffers; every rank maps every peer."""
+        """Exchange CUDA IPC handles of the peer-visible buffers; every rank maps every peer."""
         import torch.distributed as dist
         mine = []
-        for which in (0, 1):
+        for which in range(capi.PEER_BUFS):
             buf = C.create_string_buffer(64)
             capi.check(self._lib.emme_ipc_export(self._h, which, buf))
             mine.append(buf.raw)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self._group)
         for r, handles in enumerate(everyone):
-            for which in (0, 1):
+            for which in range(capi.PEER_BUFS):
                 capi.check(self._lib.emme_ipc_import(self._h, r, self.world, which,
                                                      C.create_string_buffer(handles[which], 64)))
+        dist.barrier(group=self._group)          # nobody starts storing before everyone has mapped
 
+    def close(self):
+        import torch.distributed as dist
+        if getattr(self, "_h", None) and self.exchange == "p2p" and dist.is_initialized():
+            self.synchronize()
+            dist.barrier(group=self._group)      # peers may still be storing into my buffers
+        super().close()
+
+    __del__ = EigenSolver.close
+
+    # ---- exchange="allreduce" (NCCL baseline): begin / complete / finish ----
     def _complete(self):
-        """Make eigen_matrix complete on every rank."""
         import torch
         import torch.distributed as dist
-        if self.world == 1:
-            return
-        self.synchronize()                       # my kernel (and its peer stores) has finished
-        if self.exchange == "p2p":
-            dist.barrier(group=self._group)      # ... and so has everyone else's
-            return
+        self.synchronize()
         t = device_view(self, 0, self._device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group)
         torch.cuda.current_stream().synchronize()
 
     def seed(self, omega0):
+        if self.exchange != "allreduce":
+            return super().seed(omega0)          # p2p: the exchange is inside the library call
         w = complex(omega0)
         capi.check(self._lib.emme_seed_begin(self._h, w.real, w.imag))
         self._complete()
@@ -248,8 +324,8 @@ class ShardedEigenSolver(EigenSolver):
         capi.check(self._lib.emme_seed_finish(self._h))
         self._pull()
 
-    def newtonTraceSecantIteration(self):
-        rc = self._lib.emme_step_begin(self._h)
+    def _step(self, begin):
+        rc = begin(self._h)
         self._pull()
         capi.check(rc)
         self._complete()
@@ -257,11 +333,75 @@ class ShardedEigenSolver(EigenSolver):
         capi.check(self._lib.emme_step_finish(self._h, *[C.byref(x) for x in v]))
         self._pull()
 
+    def newtonTraceSecantIteration(self):
+        if self.exchange != "allreduce":
+            return super().newtonTraceSecantIteration()
+        self._step(self._lib.emme_step_begin)
+
     def newtonQRSecantIteration(self):
-        rc = self._lib.emme_qr_step_begin(self._h)
-        self._pull()
-        capi.check(rc)
-        self._complete()
-        v = [C.c_double() for _ in range(4)]
-        capi.check(self._lib.emme_step_finish(self._h, *[C.byref(x) for x in v]))
-        self._pull()
+        if self.exchange != "allreduce":
+            return super().newtonQRSecantIteration()
+        self._step(self._lib.emme_qr_step_begin)
+
+
+class LocalShardedGroup:
+    """The ShardedEigenSolver protocol driven from ONE process: `world` handles (rank r on
+    devices[r]; several ranks may share a device) attached to each other with emme_peer_attach, one
+    host thread per rank for the calls that synchronise (seed, iterates).  Every rank ends with the
+    same eigen_value; `ranks[r]` are plain EigenSolver objects for inspection."""
+
+    def __init__(self, params, npoints, eta, g, bi, devices, shard_dense=True):
+        self.world = len(devices)
+        self.ranks = [EigenSolver(params, npoints, eta, g, bi, device=d) for d in devices]
+        lib = self.ranks[0]._lib
+        for r, s in enumerate(self.ranks):
+            s.shard_config(r, self.world)
+        for r, s in enumerate(self.ranks):
+            for q, peer in enumerate(self.ranks):
+                capi.check(lib.emme_peer_attach(s._h, q, self.world, peer._h))
+        self.dense_sharded = False
+        if shard_dense:
+            for s in self.ranks:
+                capi.check(lib.emme_shard_dense(s._h, 1))
+            self.dense_sharded = True
+
+    def _all(self, fn):
+        import threading
+        errs = [None] * self.world
+
+        def run(r):
+            try:
+                fn(self.ranks[r])
+            except Exception as e:  # noqa: BLE001 - re-raised below on the calling thread
+                errs[r] = e
+        th = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+
+    def seed(self, omega0):
+        self._all(lambda s: s.seed(omega0))
+
+    def newtonTraceSecantIteration(self):
+        self._all(lambda s: s.newtonTraceSecantIteration())
+
+    def newtonQRSecantIteration(self):
+        self._all(lambda s: s.newtonQRSecantIteration())
+
+    @property
+    def eigen_value(self):
+        return self.ranks[0].eigen_value
+
+    @property
+    def d_eigen_value(self):
+        return self.ranks[0].d_eigen_value
+
+    def close(self):
+        for s in self.ranks:
+            s.synchronize()
+        for s in self.ranks:
+            s.close()

@@ -33,6 +33,10 @@ extern "C" {
 #define EMME_E_BAD_ORDER 1002   /* integration_start_points not 15 or 31            */
 #define EMME_E_STATE 1003       /* call sequence error (e.g. step before seed)      */
 #define EMME_E_INPUT 1004       /* input.json error; text in emme_last_error()      */
+#define EMME_E_NONFINITE 1005   /* Newton step -1/trace (or omega) is zero-divided / not finite:
+                                   "Linear solve failed." like include/solver.h:142-153; omega and
+                                   delta are updated as the reference does, nothing is assembled  */
+#define EMME_E_PEER 1006        /* multi-GPU exchange: a peer did not arrive (timeout) / bad mapping */
 
 /* The scalars the hot path reads from the reference's Parameters object
  * (include/Parameters.h:15-43) plus the mesh spacing of Grid<double> (include/Grid.h:11). */
@@ -139,13 +143,31 @@ int emme_step_begin(emme_solver* s);                           /* dense step, om
 int emme_qr_step_begin(emme_solver* s);                        /* same for the QR-secant iterate */
 int emme_step_finish(emme_solver* s, double* wr, double* wi, double* dr, double* di);
 void* emme_matrix_device_ptr(emme_solver* s, int which);
-/* Fused exchange (no collective): export the CUDA IPC handles (64 bytes each) of the two physical
- * buffers eigen_matrix / eigen_matrix_old alternate between, import every peer's handles, and
- * from then on the assembly kernel stores each entry it computes straight into the matrix of
- * EVERY GPU over NVLink.  The caller only needs a barrier after begin/middle (all ranks done
- * writing) before finish.  Up to 8 peers (one NVSwitch box). */
+/* Peer group (up to 8 GPUs of one NVSwitch box) -- fused compute + exchange, no collective library.
+ * Every rank exports the CUDA IPC handles (64 bytes each) of the buffers below and imports every
+ * peer's (its own rank included, with any bytes); once all are mapped
+ *   - the assembly kernel stores each entry it computes straight into the matrix of EVERY GPU over
+ *     NVLink, bracketed by two stream-ordered device barriers (release/acquire flags in peer memory):
+ *     emme_seed / emme_newton_trace_step / emme_newton_qr_step then work unchanged on every rank and
+ *     all ranks hold the full matrices and the same eigen_value;
+ *   - emme_shard_dense(s, 1) also shards the dense step (include/solver.h:129-140) by column blocks:
+ *     panels travel by peer stores and ready flags, the trace is bitwise the single-GPU one.
+ * emme_peer_attach does the same for handles that live in ONE process (plain pointers, peer access
+ * enabled when the devices differ): several ranks per device, each driven by its own host thread. */
+#define EMME_MAX_PEER_RANKS 8
+#define EMME_PEER_BUF_MATRIX0 0 /* first physical buffer of eigen_matrix / eigen_matrix_old  */
+#define EMME_PEER_BUF_MATRIX1 1 /* second one (they swap roles every iterate)                */
+#define EMME_PEER_BUF_FLAGS 2   /* flag page: barrier epochs, panel-ready flags, mailbox      */
+#define EMME_PEER_BUF_W 3       /* factorisation work matrix                                  */
+#define EMME_PEER_BUF_Y 4       /* M = L^-1                                                   */
+#define EMME_PEER_BUF_WS 5      /* per-tile partial traces                                    */
+#define EMME_PEER_BUFS 6
 int emme_ipc_export(emme_solver* s, int which, void* handle64);
 int emme_ipc_import(emme_solver* s, int peer_rank, int peer_count, int which, const void* handle64);
+int emme_peer_attach(emme_solver* s, int peer_rank, int peer_count, emme_solver* peer);
+int emme_shard_dense(emme_solver* s, int enable);
+/* seconds a device-side wait for a peer may spin before the call fails with EMME_E_PEER (default 20) */
+int emme_peer_set_timeout(double seconds);
 
 /* EigenSolver::nullSpace (include/solver.h:58-112): the eigenvector, i.e. the right singular
  * vector of eigen_matrix for its smallest singular value (dim complex128 to host_out), by
@@ -157,7 +179,7 @@ int emme_null_space(emme_solver* s, void* host_out);
 /* which: 0 = eigen_matrix, 1 = eigen_matrix_old, 2 = eigen_matrix_derivative
  * (the three public matrices of EigenSolver, include/solver.h:392-394). */
 int emme_copy_matrix(emme_solver* s, int which, void* host_out);
-/* Asynchronous variant of emme_copy_matrix for PINNED host memory: the copy is ordered after
+/* Asynchronous variant of emme_copy_matrix (which = 0 or 1 only) for PINNED host memory: the copy is ordered after
  * the work that produced the matrix and runs on its own stream, so it overlaps the next
  * iterate (eigen_matrix is not overwritten before the iterate after next; the handle makes the
  * overwriting assembly wait for the copy).  emme_copy_wait blocks until the data has landed. */
@@ -189,8 +211,9 @@ int emme_input_tables(const emme_input* in, double* eta, double* g, double* bi);
  * eta' = v_para/(qR) and carry a complex weight; every Runge-Kutta stage is
  * put_velocity (include/solver_pic.h:76-135) + update (:137-151) + solve_field (:251-354),
  * three stages per Integrator::step (:423-434).  On the device one kernel per stage does
- * gather + velocity + push + Bessel/phase + deposit for every marker and the last CTA turns the
- * deposited density into the new field.
+ * gather + velocity + push + Bessel/phase + deposit for every marker into per-CTA partial
+ * densities; a second small kernel (pic_field_kernel) sums them in a fixed order and turns the
+ * density into the new field.
  * ====================================================================================== */
 
 /* The members of Parameters that PIC_State reads. */

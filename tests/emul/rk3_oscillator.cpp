@@ -1,4 +1,4 @@
-// tests/emul/rk3_oscillator.cpp -- TEST PROGRAM: emme::RungeKutta3 (emme_b200/host/integrator.hpp)
+// tests/emul/rk3_oscillator.cpp -- TEST PROGRAM: emme::RungeKutta3 (tests/emul/integrator.hpp)
 // on the harmonic oscillator x'' = -x of the reference's test/test_integrator.cpp, fixed step and
 // step_adaptive, checked (i) against sin t with the reference test's own 1e-5 bound and (ii) bit
 // for bit against what the reference's Integrator template produced for the same state
@@ -10,9 +10,9 @@
 #include <limits>
 #include <vector>
 
-#include "../../emme_b200/host/integrator.hpp"
+#include "integrator.hpp"
 
-// x'' = -x as a state for emme::RungeKutta3 (interface: emme_b200/host/integrator.hpp)
+// x'' = -x as a state for emme::RungeKutta3 (interface: tests/emul/integrator.hpp)
 struct Oscillator {
     using value_type = double;
     struct velocity_type {

@@ -26,16 +26,23 @@ def main():
         single.newtonTraceSecantIteration()
     A1 = single.eigen_matrix
     ok = True
-    for exchange in ("p2p", "allreduce"):
-        s = parallel.ShardedEigenSolver(p, n, *inp.tables(), device=local, exchange=exchange)
+    # p2p + column-sharded dense step (EMME_DENSE_NBO=64 from the test gives these small matrices
+    # several column blocks per rank), p2p with a replicated dense step, NCCL all-reduce baseline
+    for exchange, shard_dense in (("p2p", True), ("p2p", False), ("allreduce", False)):
+        s = parallel.ShardedEigenSolver(p, n, *inp.tables(), device=local, exchange=exchange,
+                                        shard_dense=shard_dense)
         s.seed(w0)
-        for _ in range(3):
+        for k in range(3):
+            if rank == k % world:
+                import time
+                time.sleep(0.3)                  # ranks out of step: the device barriers must hold
             s.newtonTraceSecantIteration()
         same_w = s.eigen_value == single.eigen_value and s.d_eigen_value == single.d_eigen_value
-        same_A = np.array_equal(s.eigen_matrix, A1)
-        print(f"[rank {rank}] {case} {exchange}: omega {s.eigen_value!r} same_omega={same_w} same_matrix={same_A}",
-              flush=True)
-        ok = ok and same_w and same_A
+        same_A = np.array_equal(s.eigen_matrix, A1) and np.array_equal(s.eigen_matrix_old, single.eigen_matrix_old)
+        st = s.stats()
+        print(f"[rank {rank}] {case} {exchange} shard_dense={shard_dense}: omega {s.eigen_value!r} "
+              f"same_omega={same_w} same_matrix={same_A} sym_steps={st['sym_steps']}", flush=True)
+        ok = ok and same_w and same_A and st["sym_steps"] == 3
         s.close()
         dist.barrier()
     # scan-parallel: 6 independent k_rho points dealt to the ranks, gathered in scan order

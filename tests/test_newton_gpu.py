@@ -375,3 +375,128 @@ def test_async_matrix_download_overlaps_and_matches(native_lib):
     capi.check(s._lib.emme_copy_wait(s._h))
     got = pin.numpy().view(np.complex128).reshape(s.dim, s.dim)
     assert np.array_equal(got, want)
+
+
+def test_iterating_past_convergence_is_an_error_not_a_fault(native_lib):
+    """30 iterates on one point go far past convergence: A == A_old, A' = 0, the
+    trace vanishes and -1/trace is not finite.  The reference divides unchecked
+    (include/solver.h:139) and fails later in LAPACK; here the step that produces the non-finite
+    delta returns EMME_E_NONFINITE ("Linear solve failed ..."), nothing is assembled at a
+    non-finite omega, no CUDA error occurs and the handle stays usable."""
+    from emme_b200 import EmmeError, capi
+    inp = Input(cases.input_path("c1_n64"))
+    s = EigenSolver.from_input(inp)
+    s.seed(inp.initial_guess())
+    tol = inp.number("iteration_precision")
+    converged_at, failed_at = None, None
+    for k in range(30):
+        try:
+            s.newtonTraceSecantIteration()
+        except EmmeError as e:
+            assert e.code == capi.E_NONFINITE, (e.code, str(e))
+            assert "Linear solve failed" in str(e)
+            failed_at = k
+            break
+        if converged_at is None and abs(s.d_eigen_value) < abs(tol * s.eigen_value):
+            converged_at = k
+    assert converged_at is not None and converged_at <= 8
+    assert failed_at is not None and failed_at > converged_at, (converged_at, failed_at)
+    assert not np.isfinite(abs(s.eigen_value))           # omega was updated like the reference does
+    with pytest.raises(EmmeError):                        # and nothing assembles at that omega
+        s.newtonTraceSecantIteration()
+    # the device is healthy: a fresh seed on the same handle reproduces the reference iterates
+    w, its, _ = solve_once_eigen(inp, inp.initial_guess(), solver=s)
+    assert abs(its[-1][1]) < abs(tol * w)
+
+
+@pytest.mark.parametrize("dim,path", [(96, "sym"), (96, "lu"), (300, "lu")])
+def test_non_finite_matrix_reports_an_error(dim, path, native_lib):
+    """A NaN anywhere in A must come back as EMME_E_NONFINITE from every path of kernel 2: the
+    pivot search of the pivoting LU orders NaN candidates (it used to leave the search without a
+    winner and use 0x7fffffff as a row index)."""
+    from emme_b200 import EmmeError, capi
+    A, B = _sym_case(dim, seed=5)
+    if path == "lu":
+        A = A + np.triu(np.ones((dim, dim)), 1) * 1e-3          # not symmetric: LU paths
+    A[dim // 2, :] = np.nan
+    A[:, dim // 2] = np.nan
+    s = _trace_solver(dim)
+    with pytest.raises(EmmeError) as ei:
+        s.trace_delta(A, B)
+    assert ei.value.code == capi.E_NONFINITE, (ei.value.code, str(ei.value))
+    A2, B2 = _sym_case(dim, seed=6)                               # same handle, healthy afterwards
+    d = s.trace_delta(A2, B2)
+    assert abs(d + 1.0 / np.trace(np.linalg.solve(A2, B2))) <= 1e-11 * abs(d)
+
+
+def test_zero_rhs_reports_an_error(native_lib):
+    """A' = 0 (two identical assemblies): trace = 0 exactly, -1/0 is reported, not returned."""
+    from emme_b200 import EmmeError, capi
+    A, _ = _sym_case(128, seed=7)
+    s = _trace_solver(128)
+    with pytest.raises(EmmeError) as ei:
+        s.trace_delta(A, np.zeros_like(A))
+    assert ei.value.code == capi.E_NONFINITE
+
+
+@pytest.mark.parametrize("dim", [2304, 3000])
+def test_blocked_symmetric_path_independent_of_outer_block(dim, native_lib, monkeypatch):
+    """The blocked (outer block > 32) symmetric path forms M = L^-1 per outer block through
+    M_KK; different outer widths are different summation orders of the same quantity."""
+    A, B = _sym_case(dim, seed=8)
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    got = []
+    for nbo in ("64", "128", "256"):
+        monkeypatch.setenv("EMME_DENSE_NBO", nbo)
+        s = _trace_solver(dim)
+        d = s.trace_delta(A, B)
+        assert s.stats()["sym_steps"] == 1
+        assert abs(d - ref) <= 1e-12 * abs(ref), (nbo, d, ref)
+        got.append(d)
+        s.close()
+    monkeypatch.setenv("EMME_DENSE_NBO", "0")
+    _trace_solver(4).close()                 # restore the default outer block (process-wide setting)
+
+
+@pytest.mark.parametrize("k", [9, 27, 63])
+def test_c5_points_match_reference(k, native_lib):
+    """BASELINE configs[4] (64 independent wavenumbers, N=1024): the iterate lists of the unmodified
+    reference for three of the points (tests/golden/c5.json from make_c5_goldens.py) -- a
+    10-iterate wandering trajectory (k=9), the 4-iterate neighbour of C1 (k=27), and a point on
+    which the reference itself fails at iterate 3 with "Linear solve failed" (k=63), which the
+    scan records as NaN (src/main.cpp:311-318)."""
+    import json
+    from emme_b200 import EmmeError, workloads
+    gold = json.loads((cases.GOLD / "c5.json").read_text())["points"][str(k)]
+    k_rho, w0, txt = workloads.c5_point(k)
+    assert k_rho == gold["k_rho"] and [w0.real, w0.imag] == gold["omega0"]
+    inp = Input(text=txt)
+    s = EigenSolver.from_input(inp)
+    if "final" in gold:
+        w, its, _ = solve_once_eigen(inp, w0, solver=s)
+        assert len(its) == gold["final"][2]
+        for (wi, di), g in zip(its, gold["iterates"]):
+            wg = complex(g[0], g[1])
+            # a wandering trajectory amplifies rounding-level matrix differences through the secant
+            # quotient; the converged value is what the 1e-8 bar is about
+            assert abs(wi - wg) <= 1e-6 * abs(wg), (k, wi, wg)
+        wf = complex(gold["final"][0], gold["final"][1])
+        assert abs(w - wf) <= 1e-8 * abs(wf), (w, wf)
+    else:
+        s.seed(w0)
+        n_ok = 0
+        with pytest.raises(EmmeError) as ei:
+            for g in gold["iterates"] + [None]:
+                s.newtonTraceSecantIteration()
+                wg = complex(g[0], g[1])
+                assert abs(s.eigen_value - wg) <= 1e-7 * abs(wg), (k, n_ok, s.eigen_value, wg)
+                n_ok += 1
+        assert n_ok == len(gold["iterates"]), (n_ok, str(ei.value))
+        recs = parallel_scan_one(txt, w0)
+        assert recs[0]["eigenvalue"] == "NaN"
+    s.close()
+
+
+def parallel_scan_one(txt, w0):
+    from emme_b200 import parallel
+    return parallel.solve_scan_texts([txt], [w0])

@@ -169,7 +169,7 @@ def test_stage_kernel_algebra_matches_reference(case, emul, native_lib):
 def test_integrator_template_matches_reference(tmp_path):
     """BASELINE configs[1] names the reference's test/test_integrator.cpp: it exercises the
     Runge-Kutta `Integrator` template (not the quadrature) on x'' = -x and no longer compiles
-    against the current header.  emme::RungeKutta3 (emme_b200/host/integrator.hpp) runs the same
+    against the current header.  emme::RungeKutta3 (tests/emul/integrator.hpp) runs the same
     two loops -- fixed dt = 0.01 and step_adaptive with bounds 1e-5/1e-7 up to t = 10 -- and must
     (i) stay within the test's own 1e-5 of sin t and (ii) reproduce bit for bit what the
     reference's template produced for the same state (tests/golden/oscillator_rk3.bin)."""
