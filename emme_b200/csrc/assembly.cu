@@ -434,4 +434,16 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
     return cudaGetLastError();
 }
 
+cudaError_t assembly_preload() {
+    cudaFuncAttributes a;
+    const void* ks[] = {(const void*)assemble_kernel<15>, (const void*)assemble_kernel<31>,
+                        (const void*)node_table_kernel<15>, (const void*)node_table_kernel<31>,
+                        (const void*)diagonal_kernel};
+    for (const void* k : ks) {
+        cudaError_t e = cudaFuncGetAttributes(&a, k);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace emme

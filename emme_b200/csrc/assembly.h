@@ -28,6 +28,9 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
                             unsigned long long* n_launches, int refill_min, void* node_table);
 
+// load the kernels of assembly.cu now (see dense_preload in dense.h)
+cudaError_t assembly_preload();
+
 // scratch for the table of node_const() of the first bisection levels; launch_assembly rebuilds
 // it at the start of every assembly (its entries depend on omega and arc_coeff)
 size_t assembly_node_table_bytes(int order);

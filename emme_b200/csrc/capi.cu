@@ -264,7 +264,11 @@ static int ensure_newton_buffers(emme_solver* s) {
     if (s->use_sym) {
         if (!s->Y) CU(cudaMalloc(&s->Y, s->bytes()));
         if (!s->YT) CU(cudaMalloc(&s->YT, s->bytes()));
-        if (!s->d_sym_ws) CU(cudaMalloc(&s->d_sym_ws, emme::dense_sym_workspace_bytes(s->dim)));
+        if (!s->d_sym_ws) {   // peer-visible in the sharded dense step: at least one 2 MiB block of its own
+            size_t wsb = emme::dense_sym_workspace_bytes(s->dim);
+            if (wsb < (2u << 20)) wsb = 2u << 20;
+            CU(cudaMalloc(&s->d_sym_ws, wsb));
+        }
     }
     return 0;
 }
@@ -574,13 +578,20 @@ static int assemble_current(emme_solver* s) {
 static int ensure_peer_buffers(emme_solver* s) {
     int rc = ensure_newton_buffers(s);
     if (rc) return rc;
+    // every kernel the peer protocol can launch is loaded before the first device-side wait exists
+    CU(emme::assembly_preload());
+    CU(emme::dense_preload());
+    CU(emme::peer_preload());
     if (!s->phys[0]) {
         s->phys[0] = s->A;
         s->phys[1] = s->Aold;
     }
     if (!s->flag_page) {
-        CU(cudaMalloc(&s->flag_page, sizeof(unsigned long long) * emme::PEER_PAGE_WORDS));
-        CU(cudaMemset(s->flag_page, 0, sizeof(unsigned long long) * emme::PEER_PAGE_WORDS));
+        // a 2 MiB allocation of its own: small cudaMalloc blocks share pages, and an exported page
+        // should expose nothing but the flags
+        static_assert(sizeof(unsigned long long) * emme::PEER_PAGE_WORDS <= (2u << 20), "flag page size");
+        CU(cudaMalloc(&s->flag_page, 2u << 20));
+        CU(cudaMemset(s->flag_page, 0, 2u << 20));
     }
     return 0;
 }
@@ -943,12 +954,12 @@ int emme_null_space(emme_solver* s, void* host_out) {
 
 void* emme_matrix_device_ptr(emme_solver* s, int which) {
     if (!s) return nullptr;
-    return which == 0 ? s->A : which == 1 ? s->Aold : which == 2 ? s->Ad : nullptr;
+    return which == 0 ? s->A : which == 1 ? s->Aold : which == 2 ? s->Ad : which == 3 ? s->W : which == 4 ? s->Y : nullptr;
 }
 
 int emme_copy_matrix(emme_solver* s, int which, void* host_out) {
     if (!s) return fail(-1, "null handle");
-    if (which < 0 || which > 2) return fail(-2, "emme_copy_matrix: which must be 0, 1 or 2");
+    if (which < 0 || which > 4) return fail(-2, "emme_copy_matrix: which must be 0 .. 4");
     if (!host_out) return fail(-3, "null output");
     void* src = emme_matrix_device_ptr(s, which);
     if (!src) return fail(EMME_E_STATE, "matrix not allocated yet (call emme_seed first)");

@@ -719,7 +719,7 @@ __device__ __forceinline__ z_t zrecip_fast(z_t a) {
 //      the pivot chain.  In-place Gauss-Jordan: the identity is carried along in the part of the
 //      block the elimination has already left, every row i > c is updated over ALL columns
 //      (a_ik -= l a_ck; column c itself becomes -l), so the block ends as
-//      Mi = L11^-1 (strictly lower) \ U11 (diagonal and above); L11 goes to a second array;
+//      Mi = L11^-1 (strictly lower) \ U11 (diagonal and above);
 //   2. row CTAs [0, n_row_ctas): T = A21 Mi^T on the FP64 tensor cores.  U11 = D L11^T (symmetry)
 //      makes T[r][c] the entry a_rc just before column c is eliminated, hence
 //         L[r, c] = T[r][c] / u_cc,   U[k0+c, r] = T[r][c]   (U12 = D L21^T: no block-row solve)
@@ -734,7 +734,7 @@ constexpr int PS_ROWS = 64;                       // largest tile
 constexpr int PS_LD = NB + 4;                     // stride of sG, sL, sM, row tile: 4 (mod 8) elements
 constexpr int PS_LDY_MAX = PS_ROWS + 2;           // stride of the Y tile: tile + 2 = 2 (mod 8) elements
 constexpr int PS_TILE = PS_ROWS * PS_LD > NB * PS_LDY_MAX ? PS_ROWS * PS_LD : NB * PS_LDY_MAX;
-constexpr size_t PS_SMEM_BYTES = sizeof(z_t) * (3 * NB * PS_LD + PS_TILE) + sizeof(z_t) * NB + sizeof(double) * NB;
+constexpr size_t PS_SMEM_BYTES = sizeof(z_t) * (2 * NB * PS_LD + PS_TILE) + sizeof(z_t) * NB + sizeof(double) * NB;
 
 #ifdef EMME_PS_CLOCKS
 __device__ long long g_ps_clocks[8];   // scratch/panel_bench.cu: phase boundaries of CTA 0
@@ -745,12 +745,11 @@ __device__ long long g_ps_clocks[8];   // scratch/panel_bench.cu: phase boundari
 
 __global__ void __launch_bounds__(128)
 panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int k0, int jb, int ycol0, int ycols,
-                 int n_row_ctas, int tile, double tau, int* __restrict__ flag) {
+                 int n_row_ctas, int tile, double tau, int* __restrict__ flag, z_t* __restrict__ dvec) {
     static_assert(NB == 32, "thread mapping of the diagonal-block factorisation");
     extern __shared__ __align__(16) unsigned char ps_smem_raw[];
     z_t* sG = reinterpret_cast<z_t*>(ps_smem_raw);   // [NB][PS_LD] Gauss-Jordan work array
-    z_t* sL = sG + NB * PS_LD;                        // [NB][PS_LD] L11
-    z_t* sM = sL + NB * PS_LD;                        // [NB][PS_LD] Mi with explicit unit diagonal
+    z_t* sM = sG + NB * PS_LD;                        // [NB][PS_LD] Mi with explicit unit diagonal
     z_t* sT = sM + NB * PS_LD;                        // operand tile
     z_t* sInv = sT + PS_TILE;                         // 1/u_cc
     double* sAbs = reinterpret_cast<double*>(sInv + NB);   // |u_cc| (cabs1)
@@ -834,10 +833,7 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
             __syncwarp();   // the four threads of a row have read a_ic before one of them overwrites it
             if (gi > c && in_block) {
                 const z_t l = zmul(num, inv);
-                if (mine) {
-                    if (fabs(num.x) + fabs(num.y) > tau * ua) bad = 1;
-                    sL[gi * PS_LD + c] = l;
-                }
+                if (mine && fabs(num.x) + fabs(num.y) > tau * ua) bad = 1;
 #pragma unroll
                 for (int e = 0; e < NB / 4; ++e) zfms(x[e], l, pv[e]);
 #pragma unroll
@@ -856,14 +852,12 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
     cp_async_wait<0>();
     __syncthreads();
     PS_CLOCK(3);
-    if (blockIdx.x == 0) {
-        // the factored diagonal block goes back to W (L11 strictly below, U11 on and above the diagonal)
-        for (int e = tid; e < NB * NB; e += 128) {
-            const int rr = e / NB, cc = e % NB;
-            if (rr < jb && cc < jb)
-                W[(size_t)(k0 + rr) * ld + k0 + cc] = cc < rr ? sL[rr * PS_LD + cc] : sG[rr * PS_LD + cc];
-        }
-    }
+    // Every CTA of this launch reads the UNFACTORED diagonal block from W (above) whenever it gets
+    // scheduled -- with more CTAs than fit the device at once, or a device shared with other streams,
+    // that can be long after CTA 0 has finished.  The block is therefore never written back in place
+    // (round 1 did, a latent race); nothing downstream reads L11 / U11, only the pivots d_k = u_kk,
+    // which go to their own vector.
+    if (blockIdx.x == 0 && tid < jb) dvec[k0 + tid] = sG[tid * PS_LD + tid];
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int rg = tile >> 4;                     // 16-row groups per tile: 1, 2 or 4
@@ -979,10 +973,10 @@ zgemm_sym2_kernel(z_t* __restrict__ C1, const z_t* __restrict__ B1, int M1, int 
     }
 }
 
-// YT(i, k) = Y(k, i) / d_k for k >= i (d = diag of the factored W), zero below the diagonal (only
+// YT(i, k) = Y(k, i) / d_k for k >= i (d = the pivots, dvec), zero below the diagonal (only
 // the diagonal 64-blocks are ever read there).  32 x 32 tiles, block (32, 8).
 __global__ void __launch_bounds__(256)
-transpose_invd_kernel(const z_t* __restrict__ Y, const z_t* __restrict__ W, z_t* __restrict__ YT, int dim) {
+transpose_invd_kernel(const z_t* __restrict__ Y, const z_t* __restrict__ dvec, z_t* __restrict__ YT, int dim) {
     __shared__ z_t t[32][33];
     const int bi = blockIdx.y, bk = blockIdx.x;
     if (bk < bi) {
@@ -997,7 +991,7 @@ transpose_invd_kernel(const z_t* __restrict__ Y, const z_t* __restrict__ W, z_t*
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int k = bk * 32 + r, i = bi * 32 + threadIdx.x;
         z_t v = make_double2(0., 0.);
-        if (k < dim && i < dim && k >= i) v = zmul(Y[(size_t)k * dim + i], zrecip(W[(size_t)k * dim + k]));
+        if (k < dim && i < dim && k >= i) v = zmul(Y[(size_t)k * dim + i], zrecip(dvec[k]));
         t[r][threadIdx.x] = v;
     }
     __syncthreads();
@@ -1097,6 +1091,12 @@ __global__ void reduce_partials_kernel(const z_t* __restrict__ partial, int n, z
     if (threadIdx.x == 0) *out = make_double2(sx[0], sy[0]);
 }
 
+struct ShardPtrs;
+__global__ void ydiag_kernel(const ShardPtrs sp, z_t* __restrict__ S, int ld, int dim, int K0, int JB, int blk0, int P,
+                             int nbo);
+__global__ void shard_update_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, const z_t* __restrict__ S, int ld, int dim,
+                                    int K0, int JB, int wblk0, int nwt, int yblk0, int P, int nbo);
+
 static cudaError_t gemm_setup() {
     static bool done = false;
     if (done) return cudaSuccess;
@@ -1112,6 +1112,10 @@ static cudaError_t gemm_setup() {
     e = cudaFuncSetAttribute(ptrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(panel_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ydiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(shard_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
@@ -1443,24 +1447,32 @@ cudaError_t launch_trace_solve(void* Wv, void* Bv, int dim, void* workspace, voi
 struct ShardPtrs {
     z_t* W[EMME_MAX_PEERS];
     z_t* Y[EMME_MAX_PEERS];
+    z_t* dvec[EMME_MAX_PEERS];
     int n, me;
 };
 
-// Copy panel K to every other rank: W[K0:dim, K0:KE) (L panel, factored diagonal block included),
-// W[K0:KE, KE:dim) (U12) and Y[K0:KE, K0:KE) (M_KK).  Row-contiguous 16-byte accesses.
+// Copy panel K to every other rank: W[KE:dim, K0:KE) (L panel below the diagonal block),
+// W[K0:KE, KE:dim) (U12), Y[K0:KE, K0:KE) (M_KK) and the pivots d[K0:KE).  Row-contiguous 16-byte accesses.
 __global__ void __launch_bounds__(256)
 publish_panel_kernel(const ShardPtrs sp, int ld, int dim, int K0, int JB) {
     const int KE = K0 + JB;
-    const size_t n1 = (size_t)(dim - K0) * JB;          // L panel
+    const size_t n1 = (size_t)(dim - KE) * JB;          // L panel
     const size_t n2 = (size_t)JB * (dim - KE);          // U12
     const size_t n3 = (size_t)JB * JB;                  // M_KK
     const size_t total = n1 + n2 + n3;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < (size_t)JB) {
+        const z_t v = sp.dvec[sp.me][K0 + gid];
+#pragma unroll
+        for (int r = 0; r < EMME_MAX_PEERS; ++r)
+            if (r < sp.n && r != sp.me) sp.dvec[r][K0 + gid] = v;
+    }
+    for (size_t e = gid; e < total; e += stride) {
         size_t off;
         bool in_y = false;
         if (e < n1) {
-            off = (size_t)(K0 + e / JB) * ld + K0 + e % JB;
+            off = (size_t)(KE + e / JB) * ld + K0 + e % JB;
         } else if (e < n1 + n2) {
             const size_t f = e - n1;
             const int w = dim - KE;
@@ -1555,10 +1567,12 @@ shard_update_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, const z_t* __restr
 }
 
 // ------------------------------------------------------------------ symmetric path: driver
-size_t dense_sym_workspace_bytes(int dim) {
+// per-tile partial traces [PTRACE_MAX_CHUNKS][ntiles], then the pivots d_k (dim entries)
+static size_t sym_ws_partials(int dim) {
     const size_t nt = (dim + GM - 1) / GM;
-    return sizeof(z_t) * (nt * (nt + 1) / 2) * PTRACE_MAX_CHUNKS + 64;
+    return (nt * (nt + 1) / 2) * PTRACE_MAX_CHUNKS;
 }
+size_t dense_sym_workspace_bytes(int dim) { return sizeof(z_t) * (sym_ws_partials(dim) + (size_t)dim) + 64; }
 
 // W <- A (lower block triangle) + bitwise symmetry check (raises bit 2 of *d_flag).  Kept apart
 // from launch_trace_sym because A alternates between two buffers while the rest of the step
@@ -1580,7 +1594,8 @@ int dense_sym_outer_block(int dim) { return g_nbo > 0 ? g_nbo : (dim <= 2048 ? N
     } while (0)
 
 // trace(A^-1 B) for complex symmetric A, W holding A's lower block triangle (destroyed: on return
-// W holds the complete L\U factors), Y and YT dim x dim scratch, B read only.  Raises bit 1 of
+// W holds L below and U = D L^T right of the diagonal blocks; the blocks themselves are left
+// unfactored, the pivots live in the workspace), Y and YT dim x dim scratch, B read only.  Raises bit 1 of
 // *d_flag when partial pivoting would have interchanged rows (the caller then repeats the step with
 // the pivoting LU).  *d_flag is NOT cleared here.
 // `peers` (may be null = one GPU): the W / Y / workspace / flag-page mappings of the ranks that share
@@ -1627,7 +1642,9 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
         sp.W[r] = peers ? (z_t*)peers->W[r] : W;
         sp.Y[r] = peers ? (z_t*)peers->Y[r] : Y;
         pd.p[r] = peers ? (z_t*)peers->ws[r] : (z_t*)sym_workspace;
+        sp.dvec[r] = pd.p[r] + sym_ws_partials(dim);
     }
+    z_t* dvec = (z_t*)sym_workspace + sym_ws_partials(dim);
     if (NBO % GN != 0 || NBO == NB) {
         // ---- single level / unaligned outer block: one GPU only (small systems, launch bound) ----
         if (P > 1) return cudaErrorInvalidValue;
@@ -1639,7 +1656,7 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                 const int ke = k0 + jb;
                 const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
                 panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, 0, ke, n_row,
-                                                                                tile, g_tau, d_flag);
+                                                                                tile, g_tau, d_flag, dvec);
                 ++nl;
                 // inside the outer block: columns [ke, KE) of W below the panel, rows [ke, KE) of Y
                 if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, 0, ke, k0, jb);
@@ -1671,12 +1688,12 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                 const int ke = k0 + jb;
                 const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke - K0 + tile - 1) / tile;
                 panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, K0, ke, n_row,
-                                                                                tile, g_tau, d_flag);
+                                                                                tile, g_tau, d_flag, dvec);
                 ++nl;
                 if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, K0, ke - K0, k0, jb);
             }
             if (P > 1) {
-                const size_t total = (size_t)(dim - K0) * JB + (size_t)JB * (dim - KE) + (size_t)JB * JB;
+                const size_t total = 2 * (size_t)(dim - KE) * JB + (size_t)JB * JB;
                 int blocks = (int)((total + 1023) / 1024);
                 if (blocks > 1184) blocks = 1184;
                 publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB);
@@ -1743,7 +1760,7 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
     // A^-1 = M^T D^-1 M on the lower block triangle, contracted with B on the fly
     {
         const int nt32 = (dim + 31) / 32;
-        transpose_invd_kernel<<<dim3(nt32, nt32), dim3(32, 8), 0, stream>>>(Y, W, YT, dim);
+        transpose_invd_kernel<<<dim3(nt32, nt32), dim3(32, 8), 0, stream>>>(Y, dvec, YT, dim);
         ++nl;
         const int nt = (dim + GM - 1) / GM;
         const int ntiles = nt * (nt + 1) / 2;
@@ -1770,6 +1787,42 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
     }
     if (n_launches) *n_launches += nl;
     return cudaGetLastError();
+}
+
+// Load every kernel of this translation unit now.  CUDA loads kernels lazily, on their first launch,
+// and that load may need the context to drain -- which never happens while a device-side wait of the
+// peer protocol is spinning for exactly the work whose launch is being loaded (a deadlock until the
+// wait gives up; seen with several ranks on one device).  Called once, before any wait can exist.
+#define EMME_TOUCH(k)                                                        \
+    do {                                                                     \
+        cudaFuncAttributes a__;                                              \
+        cudaError_t e__ = cudaFuncGetAttributes(&a__, (const void*)(k));     \
+        if (e__ != cudaSuccess) return e__;                                  \
+    } while (0)
+cudaError_t dense_preload() {
+    EMME_TOUCH(panel_nopiv_kernel<128>);
+    EMME_TOUCH(panel_kernel);
+    EMME_TOUCH(panel_cluster_kernel<CL_TPB>);
+    EMME_TOUCH(laswp_kernel);
+    EMME_TOUCH(swap_trsm_kernel);
+    EMME_TOUCH(utrsm_kernel);
+    EMME_TOUCH(zgemm_sub_kernel);
+    EMME_TOUCH(zgemm_sub2_kernel);
+    EMME_TOUCH(sym_copy_check_kernel);
+    EMME_TOUCH(set_identity_diag_kernel);
+    EMME_TOUCH(panel_sym_kernel);
+    EMME_TOUCH(zgemm_sym2_kernel);
+    EMME_TOUCH(transpose_invd_kernel);
+    EMME_TOUCH(ptrace_kernel);
+    EMME_TOUCH(reduce_partials_kernel);
+    EMME_TOUCH(trace_kernel);
+    EMME_TOUCH(secant_kernel);
+    EMME_TOUCH(conj_normalise_kernel);
+    EMME_TOUCH(publish_panel_kernel);
+    EMME_TOUCH(ydiag_kernel);
+    EMME_TOUCH(ycopy_kernel);
+    EMME_TOUCH(shard_update_kernel);
+    return cudaSuccess;
 }
 
 }  // namespace emme

@@ -54,6 +54,8 @@ void dense_set_pivot_threshold(double tau);
 cudaError_t launch_secant(const void* A, const void* Aold, void* Ad, size_t n, double dr,
                           double di, int sms, cudaStream_t stream);
 cudaError_t dense_prepare();
+// load all kernels of dense.cu now (lazy loading must not happen under a device-side peer wait)
+cudaError_t dense_preload();
 void dense_force_grid_panel(bool on);
 void dense_set_outer_block(int nbo);
 // measured DFMA throughput (TFLOP/s) of the current device

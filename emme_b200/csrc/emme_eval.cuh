@@ -505,7 +505,16 @@ EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeConst&
     const cplx L = mk(fma(ca, nc.h.re, fma(cb, nc.itaut.im, fma(-hb, il.re, nc.M.re))),
                       fma(ca, nc.h.im, fma(-cb, nc.itaut.re, fma(-hb, il.im, nc.M.im))));
     const cplx arg = L - z4;
-    if (arg.re < -40.) return mk(0., 0.);      // safe_exp underflow guard (:167-173)
+    // safe_exp underflow guard (:167-173): the exponential factor is an exact zero and the node
+    // contributes nothing -- decided BEFORE the Bessel recurrence, which is skipped (a third of all
+    // evaluations of C1).  One corner is kept faithful: the reference still multiplies its zero by
+    // (i0 y0 + i1 y1)/mu, and once the backward recurrence of bessel_i_alter_helper has overflowed
+    // (|z| beyond ~700: lambda ~ 0, only reached at Im omega < 0 far from any root) that product is
+    // 0 * inf = NaN, the matrix entry is NaN, zsysv fails and the scan records the point as "NaN"
+    // (src/main.cpp:311-318; C5 point 63, tests/golden/c5.json).  Below |z| = 500 no overflow is
+    // possible (growth <= e^|z|), above it the recurrence runs and decides.
+    const bool under = arg.re < -40.;
+    if (under && norm2(z) < 2.5e5) return mk(0., 0.);
 
     cplx y0, y1, mu;
     bessel_i_alter(z, zc, y0, y1, mu, cnt);
@@ -518,6 +527,10 @@ EMME_HD cplx eval_node(const RunConst& rc, const PC& pc, int m, const NodeConst&
     const cplx A = mk(fma(cA, nc.h.re, rc.a0), fma(cA, nc.h.im, rc.wi));
     const cplx B = rc.wsi_etai * (mk(hb, 0.) - lambda);
     const cplx S = (A + B * il2) * y0 + (pc.f_c1() * il2) * y1;
+    if (under) {
+        const double probe = (S.re + S.im) + (mu.re + mu.im);      // non-finite iff any part is
+        return (probe - probe == 0.0) ? mk(0., 0.) : mk(probe - probe, probe - probe);   // 0, or NaN like 0 * inf
+    }
 
 #if EMME_LEAN_CEXP
     const cplx se = cexp_lean(arg.re, arg.im);

@@ -95,4 +95,15 @@ cudaError_t launch_peer_collect(const PeerFlags& f, unsigned long long serial, d
     return cudaGetLastError();
 }
 
+cudaError_t peer_preload() {
+    cudaFuncAttributes a;
+    const void* ks[] = {(const void*)peer_barrier_kernel, (const void*)peer_signal_kernel, (const void*)peer_wait_kernel,
+                        (const void*)peer_post_kernel, (const void*)peer_collect_kernel};
+    for (const void* k : ks) {
+        cudaError_t e = cudaFuncGetAttributes(&a, k);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace emme

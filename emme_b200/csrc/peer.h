@@ -40,6 +40,8 @@ cudaError_t launch_peer_post(const PeerFlags& f, unsigned long long serial, cons
 // after a barrier: sum the posted values in rank order (identical on every rank), OR the flags, first info
 cudaError_t launch_peer_collect(const PeerFlags& f, unsigned long long serial, double2* d_value, int* d_flag,
                                 int* d_info, cudaStream_t stream);
+// load the kernels above now (see dense_preload)
+cudaError_t peer_preload();
 // seconds a wait may spin before it gives up (default 20; tests shorten it)
 void peer_set_timeout(double seconds);
 

@@ -55,6 +55,7 @@
 #include "../host/json.hpp"
 #include "../host/parameters.hpp"
 #include "common.h"
+#include "peer.h"
 #include "pic_eval.cuh"
 
 namespace {
@@ -64,7 +65,19 @@ using emme::d2;
 using emme::mk2;
 using emme::PicConst;
 
+// Multi-GPU density exchange without a collective library: every rank owns an exchange buffer
+// [2 parities][P ranks][nf] of partial densities followed by [P ranks][field-kernel blocks] ready
+// flags (one cudaMalloc block, mapped by every peer).  See pic_field_kernel, mode 3.
+struct PicPeers {
+    d2* xch[EMME_MAX_PEER_RANKS];                   // exchange buffer of rank r (own entry = local pointer)
+    unsigned long long* flags[EMME_MAX_PEER_RANKS]; // its flag area
+    int n, me;
+    unsigned long long timeout_ns;
+    unsigned long long* err;                         // local: a wait gave up
+};
+
 struct PicDev {
+    PicPeers peers;
     PicConst k;
     long n;
     int nf;
@@ -99,8 +112,16 @@ __device__ __forceinline__ void deposit(const PicDev& d, d2* cells, double eta, 
 // mode 0: field = coef * sum(partials); mode 1 (multi-GPU, before the exchange):
 // dens = sum(partials); mode 2 (after the exchange): field = coef * dens.  Without shared-memory
 // cells the stage kernel has already accumulated into dens, which is cleared once it is consumed.
+// mode 3 (multi-GPU, fused exchange): the block sums this rank's partials of its 32 cells, stores
+// them into slot `me` of EVERY rank's exchange buffer over NVLink, announces them with one release
+// store per peer (flag [me][block] = stage serial), waits for the same block of every other rank
+// (acquire loads of local memory) and adds the P slots in rank order -- every rank forms the same
+// field, bit for bit, with no collective call and only block-local synchronisation.  The serial is
+// 3 * (steps started) + stage, derived from the on-device step counter, so the launch is the same
+// every step (CUDA graph); the two parities of the buffer keep a fast rank's next stage out of the
+// slots a slow rank is still reading.
 #define PIC_FIELD_CHUNKS 32
-__global__ void __launch_bounds__(32 * PIC_FIELD_CHUNKS) pic_field_kernel(PicDev d, int mode, int record) {
+__global__ void __launch_bounds__(32 * PIC_FIELD_CHUNKS) pic_field_kernel(PicDev d, int mode, int record, int stage) {
     __shared__ d2 red[PIC_FIELD_CHUNKS][32];
     const int cell = blockIdx.x * 32 + threadIdx.x, ch = threadIdx.y;
     d2 acc = mk2(0.0, 0.0);
@@ -121,6 +142,42 @@ __global__ void __launch_bounds__(32 * PIC_FIELD_CHUNKS) pic_field_kernel(PicDev
     }
     red[ch][threadIdx.x] = acc;
     __syncthreads();
+    if (mode == 3) {
+        const PicPeers& pp = d.peers;
+        const unsigned long long seq = 3ull * (*d.step) + (unsigned long long)stage;   // *d.step >= 1 here
+        const size_t slot = (size_t)(seq & 1ull) * pp.n;
+        const bool mine = ch == 0 && cell < d.nf;
+        if (mine) {
+            for (int c = 1; c < PIC_FIELD_CHUNKS; ++c) {
+                acc.x += red[c][threadIdx.x].x;
+                acc.y += red[c][threadIdx.x].y;
+            }
+            if (summed) d.dens[cell] = mk2(0.0, 0.0);
+            for (int r = 0; r < pp.n; ++r) pp.xch[r][(slot + pp.me) * d.nf + cell] = acc;
+        }
+        __syncthreads();
+        if (ch == 0 && threadIdx.x < pp.n) {
+            // one thread per peer: publish my block, then wait for that peer's
+            const int r = threadIdx.x;
+            __threadfence_system();
+            emme::st_release_sys(pp.flags[r] + (size_t)pp.me * gridDim.x + blockIdx.x, seq);
+            if (!emme::spin_until(pp.flags[pp.me] + (size_t)r * gridDim.x + blockIdx.x, seq, pp.timeout_ns))
+                atomicMax(pp.err, seq);
+        }
+        __syncthreads();
+        if (!mine) return;
+        acc = mk2(0.0, 0.0);
+        for (int r = 0; r < pp.n; ++r) {          // rank order: the same sum on every rank
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(&pp.xch[pp.me][(slot + r) * d.nf + cell]));
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        const double cf = d.coef[cell];
+        const d2 f = mk2(acc.x * cf, acc.y * cf);
+        d.field[cell] = f;
+        if (record) d.hist[(*d.step - 1) * (unsigned long long)d.nf + cell] = f;
+        return;
+    }
     if (ch != 0 || cell >= d.nf) return;
     for (int c = 1; c < PIC_FIELD_CHUNKS; ++c) {
         acc.x += red[c][threadIdx.x].x;
@@ -333,7 +390,13 @@ struct emme_pic {
     void* d_coef = nullptr;
     long hist_cap = 0;
     long steps_done = 0;
-    int shard_count = 1;
+    int shard_count = 1, shard_index = 0;
+    // fused peer exchange (pic_field_kernel mode 3): one cudaMalloc block = exchange slots + flags
+    void* xch = nullptr;
+    size_t xch_flag_offset = 0;
+    void* peer_xch[EMME_MAX_PEER_RANKS] = {};
+    bool peer_ipc[EMME_MAX_PEER_RANKS] = {};
+    int peer_count = 0;       // > 1 once every rank's buffer is mapped: emme_pic_step then works sharded
     int next_call = 0;        // sharded protocol: 2*stage = begin(stage) expected, 2*stage+1 = finish(stage)
     int grid = 0;
     size_t smem = 0;
@@ -435,8 +498,9 @@ cudaError_t launch_stage(emme_pic* s, double dt, int stage) {
     return launch_pdl(s, pic_stage_kernel<false, false>, grid, block, 0, s->d, stage, h, c1, c2);
 }
 
-cudaError_t launch_field(emme_pic* s, int mode, int record) {
-    return launch_pdl(s, pic_field_kernel, dim3((s->d.nf + 31) / 32), dim3(32, PIC_FIELD_CHUNKS), 0, s->d, mode, record);
+cudaError_t launch_field(emme_pic* s, int mode, int record, int stage = 0) {
+    return launch_pdl(s, pic_field_kernel, dim3((s->d.nf + 31) / 32), dim3(32, PIC_FIELD_CHUNKS), 0, s->d, mode, record,
+                      stage);
 }
 
 }  // namespace

@@ -379,9 +379,13 @@ class LocalShardedGroup:
             t.start()
         for t in th:
             t.join()
-        for e in errs:
-            if e is not None:
-                raise e
+        bad = [(r, e) for r, e in enumerate(errs) if e is not None]
+        if bad:
+            # a rank that failed for its own reason makes its peers time out: show every rank's error
+            msg = "; ".join(f"rank {r}: [{getattr(e, 'code', type(e).__name__)}] {e}" for r, e in bad)
+            codes = {getattr(e, "code", None) for _, e in bad}
+            own = [c for c in codes if c not in (None, capi.E_PEER)]     # prefer a rank's own failure
+            raise capi.EmmeError(own[0] if own else bad[0][1].code if hasattr(bad[0][1], "code") else -1, msg)
 
     def seed(self, omega0):
         self._all(lambda s: s.seed(omega0))

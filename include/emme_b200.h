@@ -177,7 +177,8 @@ int emme_peer_set_timeout(double seconds);
 int emme_null_space(emme_solver* s, void* host_out);
 
 /* which: 0 = eigen_matrix, 1 = eigen_matrix_old, 2 = eigen_matrix_derivative
- * (the three public matrices of EigenSolver, include/solver.h:392-394). */
+ * (the three public matrices of EigenSolver, include/solver.h:392-394); for tests of the dense
+ * step also 3 = the factored work matrix (L\U of the last symmetric step), 4 = M = L^-1. */
 int emme_copy_matrix(emme_solver* s, int which, void* host_out);
 /* Asynchronous variant of emme_copy_matrix (which = 0 or 1 only) for PINNED host memory: the copy is ordered after
  * the work that produced the matrix and runs on its own stream, so it overlaps the next

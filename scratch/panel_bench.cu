@@ -33,7 +33,7 @@ int main(int argc, char** argv) {
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES>>>(W, Y, dim, dim, k0, jb, ke, n_row, tile, 4.0, flag);
+        panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES>>>(W, Y, dim, dim, k0, jb, 0, ke, n_row, tile, 4.0, flag, dvec);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;

@@ -3,6 +3,13 @@ from pathlib import Path
 
 import pytest
 
+import os
+
+# tests/test_sharded_gpu.py runs several "virtual ranks" on ONE device, each with its own stream, and
+# their device-side waits must not share a hardware queue with the kernels they wait for: ask for 32
+# queues before the CUDA context exists (the default of 8 lets unrelated streams alias)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))

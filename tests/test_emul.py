@@ -77,3 +77,32 @@ def test_lean_cexp(emul):
         ulp = np.spacing(np.abs(ref.astype(np.float64)))
         err = np.abs(got.astype(np.longdouble) - ref) / ulp
         assert float(err.max()) <= 3.0, float(err.max())
+
+
+def test_reference_nan_corner_is_reproduced(emul, native_lib):
+    """C5 point 63 (k_rho = 0.68) at the iterate where the reference fails: for the pairs (132, 842)
+    and (181, 891) of the N=1024 mesh one quadrature node has lambda ~ 0, |z| ~ 3500, the
+    reference's Bessel recurrence overflows and its safe_exp zero times inf is NaN (the entry is NaN,
+    zsysv reports a singular D, the scan records "NaN").  The kernel's arithmetic -- which skips the
+    recurrence behind the underflow guard -- must give NaN for the same pairs and finite values for
+    their neighbours, like the oracle."""
+    import oracle_lib as O
+    from emme_b200 import workloads
+    _, _, txt = workloads.c5_point(63)
+    inp = Input(text=txt)
+    p, n = inp.params()
+    eta, g, bi = inp.tables()
+    w = complex(-1.9458107725918097, -0.571341647480763)
+    dp = C.POINTER(C.c_double)
+    for (i, j), want_nan in (((132, 842), True), ((181, 891), True), ((131, 841), False), ((133, 843), False)):
+        e2, g2, b2 = (np.ascontiguousarray(t[[i, j]]) for t in (eta, g, bi))
+        out = np.zeros((2, 2), dtype=np.complex128)
+        st = (C.c_ulonglong * 8)()
+        rc = emul.emul_assemble(C.byref(p), 2, e2.ctypes.data_as(dp), g2.ctypes.data_as(dp), b2.ctypes.data_as(dp),
+                                w.real, w.imag, out.view(np.float64).ctypes.data_as(dp), st)
+        assert rc == 0
+        ref, _ = O.assemble(cases.oracle_params(p), e2, g2, b2, p.dx, w)
+        assert bool(np.isnan(ref[0, 1])) == want_nan, (i, j, ref)
+        assert bool(np.isnan(out[0, 1])) == want_nan, (i, j, out)
+        if not want_nan:
+            assert abs(out[0, 1] - ref[0, 1]) <= 1e-10 * abs(ref[0, 1]), (out, ref)

@@ -484,14 +484,18 @@ def test_c5_points_match_reference(k, native_lib):
         assert abs(w - wf) <= 1e-8 * abs(wf), (w, wf)
     else:
         s.seed(w0)
-        n_ok = 0
+        for n_ok, g in enumerate(gold["iterates"]):
+            s.newtonTraceSecantIteration()
+            wg = complex(g[0], g[1])
+            assert abs(s.eigen_value - wg) <= 1e-7 * abs(wg), (k, n_ok, s.eigen_value, wg)
+        # the next dense step is the one the reference's zsysv refuses: the matrix assembled at the
+        # last iterate holds NaN entries (overflow of the reference's Bessel recurrence, reproduced)
+        A = s.eigen_matrix
+        nan_at = sorted(map(tuple, np.argwhere(np.isnan(A)).tolist()))
+        assert nan_at == [(132, 842), (181, 891), (842, 132), (891, 181)], nan_at
         with pytest.raises(EmmeError) as ei:
-            for g in gold["iterates"] + [None]:
-                s.newtonTraceSecantIteration()
-                wg = complex(g[0], g[1])
-                assert abs(s.eigen_value - wg) <= 1e-7 * abs(wg), (k, n_ok, s.eigen_value, wg)
-                n_ok += 1
-        assert n_ok == len(gold["iterates"]), (n_ok, str(ei.value))
+            s.newtonTraceSecantIteration()
+        assert "Linear solve failed" in str(ei.value)
         recs = parallel_scan_one(txt, w0)
         assert recs[0]["eigenvalue"] == "NaN"
     s.close()
