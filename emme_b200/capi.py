@@ -104,6 +104,12 @@ PROTOTYPES = {
     "emme_pic_create": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, _dp, _dp, _dp, _dp, C.c_int, C.POINTER(_vp)]),
     "emme_pic_create_shard": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, _dp, _dp, _dp, _dp, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(_vp)]),
+    "emme_pic_pweight_sum": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, _dp, _dp, _dp]),
+    "emme_pic_create_block": (C.c_int, [C.POINTER(EmmePicParams), C.c_long, C.c_long, C.c_long, _dp, _dp, _dp, _dp,
+                                        C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "emme_pic_ipc_export": (C.c_int, [_vp, _vp]),
+    "emme_pic_ipc_import": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "emme_pic_peer_attach": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "emme_pic_destroy": (C.c_int, [_vp]),
     "emme_pic_step": (C.c_int, [_vp, C.c_double, C.c_int]),
     "emme_pic_steps_done": (C.c_long, [_vp]),

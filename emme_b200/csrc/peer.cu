@@ -4,6 +4,7 @@
 namespace emme {
 
 static unsigned long long g_timeout_ns = 20ull * 1000000000ull;
+unsigned long long peer_timeout_ns() { return g_timeout_ns; }
 void peer_set_timeout(double seconds) {
     g_timeout_ns = seconds <= 0 ? 1000000ull : (unsigned long long)(seconds * 1e9);
 }

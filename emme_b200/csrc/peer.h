@@ -44,6 +44,7 @@ cudaError_t launch_peer_collect(const PeerFlags& f, unsigned long long serial, d
 cudaError_t peer_preload();
 // seconds a wait may spin before it gives up (default 20; tests shorten it)
 void peer_set_timeout(double seconds);
+unsigned long long peer_timeout_ns();
 
 // device helpers shared with kernels that signal from their own epilogue
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {

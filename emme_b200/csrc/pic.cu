@@ -45,6 +45,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <numeric>
 #include <random>
@@ -381,8 +382,9 @@ struct emme_pic {
     emme_pic_params p{};
     long n = 0, n_total = 0, first = 0;
     PicDev d{};
-    std::vector<double> h_pw, h_vpar, h_vperp, h_coef;  // host copies for emme_pic_extras
-    std::vector<long> perm;  // device slot j holds marker perm[j] of this shard (sorted by v_perp)
+    std::vector<double> h_coef;  // host copy for emme_pic_extras
+    std::vector<long> perm;  // device slot j holds marker perm[j] of this shard (sorted by v_perp); lazily downloaded
+    long* d_perm = nullptr;
     int block = 256;
     void* d_vpar = nullptr;
     void* d_vperp = nullptr;
@@ -529,17 +531,85 @@ int emme_pic_load_markers(const emme_pic_params* p, long n, long long seed, doub
     return 0;
 }
 
-int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* eta,
-                          const double* v_para, const double* v_perp, const double* weight,
-                          int shard_index, int shard_count, int device, emme_pic** out) {
-    if (!p) return capi_fail(-1, "null params");
-    if (n_total <= 0) return capi_fail(-2, "marker count must be positive");
-    if (!eta) return capi_fail(-3, "null eta");
-    if (!v_para) return capi_fail(-4, "null v_para");
-    if (!v_perp) return capi_fail(-5, "null v_perp");
-    if (!weight) return capi_fail(-6, "null weight");
-    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return capi_fail(-7, "bad shard");
-    if (!out) return capi_fail(-10, "null output handle");
+}  // extern "C"
+
+namespace {
+
+// ---- device order: markers sorted by v_perp (counting sort on PIC_SORT_BUCKETS buckets) ----
+// The Miller recurrence of bessel_j01 runs ~ x + 12.6 x^(1/3) trips with x = (v_perp/vt) sb(eta);
+// lanes of a warp that share v_perp differ only through sb(eta), which halves the spread of trip
+// counts inside a warp.  The order of markers is otherwise free (deposits commute);
+// emme_pic_markers undoes it.  Round 1 sorted and permuted on the host (one core, 68 ms per million
+// markers with the staging copies); here the raw arrays are uploaded as they are and the device
+// does histogram -> scan -> scatter (and forms p_weight = pw * 2L/sum on the way).
+constexpr int PIC_SORT_BUCKETS = 4096;
+
+__device__ __forceinline__ int pic_bucket(double v, double scale) {
+    const double b = v * scale;
+    return b > 0 ? (b < PIC_SORT_BUCKETS - 1 ? (int)b : PIC_SORT_BUCKETS - 1) : 0;
+}
+
+__global__ void pic_sort_count_kernel(const double* __restrict__ vperp, long n, double scale,
+                                      unsigned* __restrict__ hist, unsigned* __restrict__ pos) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        pos[i] = atomicAdd(&hist[pic_bucket(vperp[i], scale)], 1u);
+}
+
+// exclusive scan of the PIC_SORT_BUCKETS counters, one block of 1024 threads (4 per thread)
+__global__ void __launch_bounds__(1024) pic_sort_scan_kernel(unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[1024];
+    const int t = threadIdx.x;
+    unsigned v[PIC_SORT_BUCKETS / 1024], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PIC_SORT_BUCKETS / 1024; ++k) {
+        v[k] = hist[t * (PIC_SORT_BUCKETS / 1024) + k];
+        sum += v[k];
+    }
+    sh[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned add = t >= o ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += add;
+        __syncthreads();
+    }
+    unsigned run = sh[t] - sum;
+#pragma unroll
+    for (int k = 0; k < PIC_SORT_BUCKETS / 1024; ++k) {
+        hist[t * (PIC_SORT_BUCKETS / 1024) + k] = run;
+        run += v[k];
+    }
+}
+
+// raw (caller's order) -> device order; pw_raw == nullptr: unit water-bag weights, pw = v_perp
+__global__ void pic_sort_scatter_kernel(long n, double scale, int identity, const unsigned* __restrict__ start,
+                                        const unsigned* __restrict__ pos, const double* __restrict__ eta_raw,
+                                        const double* __restrict__ vpar_raw, const double* __restrict__ vperp_raw,
+                                        const double* __restrict__ pw_raw, const d2* __restrict__ w_raw, double inn,
+                                        double* __restrict__ eta, double* __restrict__ vpar, double* __restrict__ vperp,
+                                        double* __restrict__ pw, d2* __restrict__ w, long* __restrict__ perm) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double vq = vperp_raw[i];
+        const long j = identity ? i : (long)start[pic_bucket(vq, scale)] + pos[i];
+        eta[j] = eta_raw[i];
+        vpar[j] = vpar_raw[i];
+        vperp[j] = vq;
+        pw[j] = (pw_raw ? pw_raw[i] : vq) * inn;      // include/solver_pic.h:229-235
+        w[j] = w_raw[i];
+        perm[j] = i;
+    }
+}
+
+// un-normalised p_weight of one marker (include/solver_pic.h:229-232)
+inline double pweight_raw(const emme_pic_params* p, double vp, double vq, double wa, double wb) {
+    return vq * std::exp(-(vp * vp * wa + vq * vq * wb) / (2 * p->vt * p->vt));
+}
+
+// The PIC_State constructor for the contiguous block [first, first + n) of n_total markers; the
+// arrays point at the BLOCK.  pw_sum is the sum of the un-normalised p_weight over ALL markers.
+int create_impl(const emme_pic_params* p, long n_total, long first, long n, const double* eta, const double* v_para,
+                const double* v_perp, const double* weight, double pw_sum, int shard_index, int shard_count,
+                int device, emme_pic** out) {
     if (p->npoints < 4) return capi_fail(-1, "npoints must be at least 4");
     if (emme_device_count() <= 0)
         return capi_fail(EMME_E_NO_DEVICE, "no CUDA device: emme_b200 has no CPU fallback");
@@ -554,11 +624,9 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     s->p = *p;
     s->n_total = n_total;
     s->shard_count = shard_count;
-    // contiguous block of markers
-    const long per = n_total / shard_count, rem = n_total % shard_count;
-    s->first = shard_index * per + (shard_index < rem ? shard_index : rem);
-    s->n = per + (shard_index < rem ? 1 : 0);
-    const long n = s->n, f0 = s->first;
+    s->shard_index = shard_index;
+    s->first = first;
+    s->n = n;
     const int nf = p->npoints;
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     CU(configure_pool(device));
@@ -578,25 +646,9 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
         tprev = t;
     };
     lap("stream + events");
-    // initialize_marker_extras (include/solver_pic.h:207-238): p_weight normalised over ALL markers
-    std::vector<double> pw(n_total);
     const double wa = 1 - p->water_bag_weight_vpara, wb = 1 - p->water_bag_weight_vperp;
-    if (wa == 0 && wb == 0) {
-        // the exponent is -0/(2 vt^2): exp gives exactly 1 for every finite marker, v_perp * 1 = v_perp
-        for (long i = 0; i < n_total; ++i) pw[i] = v_perp[i];
-    } else {
-        for (long i = 0; i < n_total; ++i) {
-            const double vp = v_para[i], vq = v_perp[i];
-            pw[i] = vq * std::exp(-(vp * vp * wa + vq * vq * wb) / (2 * p->vt * p->vt));
-        }
-    }
-    double sum = 0;
-    for (long i = 0; i < n_total; ++i) sum += pw[i];
-    const double inn = 2 * p->length / (sum);
-    s->h_pw.resize(n);
-    for (long i = 0; i < n; ++i) s->h_pw[i] = pw[f0 + i] * inn;
-    s->h_vpar.assign(v_para + f0, v_para + f0 + n);
-    s->h_vperp.assign(v_perp + f0, v_perp + f0 + n);
+    const bool unit = wa == 0 && wb == 0;
+    const double inn = 2 * p->length / pw_sum;
     // cal_quasi_neutrality_coef (include/solver_pic.h:381-399)
     const double cell_width = 2 * p->length / p->npoints;
     s->h_coef.resize(nf);
@@ -605,8 +657,14 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
         const double g0 = std::cyl_bessel_i(0, b) * std::exp(-b);
         s->h_coef[idx] = 1. / ((1. + 1. / p->tau - g0) * cell_width);
     }
-
-    lap("extras + table (host)");
+    double vmax = 0;
+    for (long i = 0; i < n; ++i) vmax = std::max(vmax, v_perp[i]);
+    std::vector<double> pw_host;
+    if (!unit) {   // glibc's exp, like the reference: formed on the host, normalised on the device
+        pw_host.resize(n);
+        for (long i = 0; i < n; ++i) pw_host[i] = pweight_raw(p, v_para[i], v_perp[i], wa, wb);
+    }
+    lap("table + v_perp range (host)");
     PicDev& d = s->d;
     d.n = n;
     d.nf = nf;
@@ -638,54 +696,41 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     CU(dev_alloc(&d.dens, nf, s->stream));
     CU(dev_alloc(&dcoef, nf, s->stream));
     CU(dev_alloc(&d.step, 1, s->stream));
+    CU(dev_alloc(&s->d_perm, n, s->stream));
     d.vpar = dvpar; d.vperp = dvperp; d.pw = dpw; d.coef = dcoef;
     s->d_vpar = dvpar; s->d_vperp = dvperp; s->d_pw = dpw; s->d_coef = dcoef;
     lap("cudaMalloc");
-    // Device order: markers sorted by v_perp.  The Miller recurrence of bessel_j01 runs
-    // ~ x + 12.6 x^(1/3) trips with x = (v_perp/vt) sb(eta); lanes of a warp that share v_perp
-    // differ only through sb(eta), which halves the spread of trip counts inside a warp.  The
-    // order of markers is otherwise free (deposits commute); emme_pic_markers undoes it.
-    s->perm.resize(n);
-    if (std::getenv("EMME_PIC_NOSORT")) {
-        std::iota(s->perm.begin(), s->perm.end(), 0L);
-    } else {
-        // counting sort on 4096 buckets of v_perp (stable, O(n)): warps only need similar values
-        const int NB = 4096;
-        double vmax = 0;
-        for (long i = 0; i < n; ++i) vmax = std::max(vmax, v_perp[f0 + i]);
-        const double scale = vmax > 0 ? (NB - 1) / vmax : 0.0;
-        std::vector<long> start(NB + 1, 0);
-        std::vector<unsigned short> bucket(n);
-        for (long i = 0; i < n; ++i) {
-            const double b = v_perp[f0 + i] * scale;
-            bucket[i] = (unsigned short)(b > 0 ? (b < NB - 1 ? (int)b : NB - 1) : 0);
-            ++start[bucket[i] + 1];
-        }
-        for (int b = 0; b < NB; ++b) start[b + 1] += start[b];
-        for (long i = 0; i < n; ++i) s->perm[start[bucket[i]]++] = i;
-    }
-    lap("counting sort (host)");
     {
-        // one uninitialised staging block (a zero-filled std::vector costs a second pass over 48 B/marker)
-        std::unique_ptr<double[]> stage(new double[6 * (size_t)n]);
-        double *t_eta = stage.get(), *t_vpar = t_eta + n, *t_vperp = t_vpar + n, *t_pw = t_vperp + n,
-               *t_w = t_pw + n;
-        for (long j = 0; j < n; ++j) {
-            const long i = f0 + s->perm[j];
-            t_eta[j] = eta[i];
-            t_vpar[j] = v_para[i];
-            t_vperp[j] = v_perp[i];
-            t_pw[j] = s->h_pw[s->perm[j]];
-            t_w[2 * j] = weight[2 * i];
-            t_w[2 * j + 1] = weight[2 * i + 1];
-        }
-        CU(cudaMemcpyAsync(d.eta, t_eta, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(dvpar, t_vpar, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(dvperp, t_vperp, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(dpw, t_pw, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(d.w, t_w, sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaStreamSynchronize(s->stream));   // the staging vectors go out of scope
-        lap("permute + upload");
+        // raw arrays in the caller's order (released to the pool once the scatter has run)
+        double *r_eta, *r_vpar, *r_vperp, *r_pw = nullptr;
+        d2* r_w;
+        unsigned *hist, *pos;
+        CU(dev_alloc(&r_eta, n, s->stream));
+        CU(dev_alloc(&r_vpar, n, s->stream));
+        CU(dev_alloc(&r_vperp, n, s->stream));
+        CU(dev_alloc(&r_w, n, s->stream));
+        CU(dev_alloc(&hist, PIC_SORT_BUCKETS, s->stream));
+        CU(dev_alloc(&pos, n, s->stream));
+        if (!unit) CU(dev_alloc(&r_pw, n, s->stream));
+        CU(cudaMemsetAsync(hist, 0, sizeof(unsigned) * PIC_SORT_BUCKETS, s->stream));
+        CU(cudaMemcpyAsync(r_vperp, v_perp, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        const bool identity = std::getenv("EMME_PIC_NOSORT") != nullptr;
+        const double scale = vmax > 0 ? (PIC_SORT_BUCKETS - 1) / vmax : 0.0;
+        const int sg = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+        pic_sort_count_kernel<<<sg, 256, 0, s->stream>>>(r_vperp, n, scale, hist, pos);   // overlaps the other uploads
+        pic_sort_scan_kernel<<<1, 1024, 0, s->stream>>>(hist);
+        CU(cudaMemcpyAsync(r_eta, eta, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(r_vpar, v_para, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(r_w, weight, sizeof(d2) * n, cudaMemcpyHostToDevice, s->stream));
+        if (!unit) CU(cudaMemcpyAsync(r_pw, pw_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+        pic_sort_scatter_kernel<<<sg, 256, 0, s->stream>>>(n, scale, identity ? 1 : 0, hist, pos, r_eta, r_vpar, r_vperp,
+                                                          r_pw, r_w, inn, d.eta, dvpar, dvperp, dpw, d.w, s->d_perm);
+        s->launches += 3;
+        CU(cudaGetLastError());
+        for (void* b : {(void*)r_eta, (void*)r_vpar, (void*)r_vperp, (void*)r_w, (void*)hist, (void*)pos, (void*)r_pw})
+            if (b) CU(cudaFreeAsync(b, s->stream));
+        CU(cudaStreamSynchronize(s->stream));   // pw_host and the caller's arrays may go away
+        lap("upload + device sort");
     }
     CU(cudaMemcpyAsync(dcoef, s->h_coef.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemsetAsync(d.field, 0, sizeof(d2) * nf, s->stream));
@@ -713,6 +758,7 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     const long want = (n + s->block - 1) / s->block;
     const long cap = (long)s->sms * per_sm;
     s->grid = (int)(want < cap ? want : cap);
+    if (s->grid < 1) s->grid = 1;
     if (const char* e = std::getenv("EMME_PIC_PERSISTENT")) s->use_persistent = std::atoi(e);
     int coop = 0;
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
@@ -734,11 +780,26 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     CU(dev_alloc(&d.part, (size_t)d.nparts * nf, s->stream));
     if (const char* e = std::getenv("EMME_PIC_GRAPH")) s->use_graph = std::atoi(e);
     if (const char* e = std::getenv("EMME_PIC_PDL")) s->use_pdl = std::atoi(e);
-    if (shard_count > 1) s->use_pdl = 0;   // an NCCL kernel sits between the stage and field kernels
+    if (shard_count > 1) {
+        s->use_pdl = 0;   // the exchange (fused, or the caller's collective) sits between the kernels of a stage
+        // exchange slots [2][P][nf] + ready flags [P][field blocks]: ONE cudaMalloc block (at least
+        // 2 MiB, so that the exported allocation holds nothing else), mapped by every peer
+        const size_t nblk = (size_t)(nf + 31) / 32;
+        s->xch_flag_offset = sizeof(d2) * 2 * (size_t)shard_count * nf;
+        s->xch_flag_offset = (s->xch_flag_offset + 255) / 256 * 256;
+        size_t bytes = s->xch_flag_offset + sizeof(unsigned long long) * ((size_t)shard_count * nblk + 1);
+        if (bytes < (2u << 20)) bytes = 2u << 20;
+        CU(cudaMalloc(&s->xch, bytes));
+        CU(cudaMemsetAsync(s->xch, 0, bytes, s->stream));
+        d.peers.n = shard_count;
+        d.peers.me = shard_index;
+        d.peers.timeout_ns = emme::peer_timeout_ns();   // emme_peer_set_timeout, 20 s by default
+        d.peers.err = reinterpret_cast<unsigned long long*>((char*)s->xch + s->xch_flag_offset) + (size_t)shard_count * nblk;
+    }
 
     const int ig = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-    if (sw) pic_init_kernel<true><<<ig, 256, 0, s->stream>>>(d);
-    else pic_init_kernel<false><<<ig, 256, 0, s->stream>>>(d);
+    if (sw) pic_init_kernel<true><<<ig > 0 ? ig : 1, 256, 0, s->stream>>>(d);
+    else pic_init_kernel<false><<<ig > 0 ? ig : 1, 256, 0, s->stream>>>(d);
     s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
@@ -748,9 +809,136 @@ int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* 
     return 0;
 }
 
+// make the host copy of the device order available (emme_pic_markers / emme_pic_extras)
+int ensure_perm(emme_pic* s) {
+    if ((long)s->perm.size() == s->n) return 0;
+    s->perm.resize(s->n);
+    CU(cudaMemcpyAsync(s->perm.data(), s->d_perm, sizeof(long) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+void set_peer(emme_pic* s, int r, void* base) {
+    s->peer_xch[r] = base;
+    s->d.peers.xch[r] = reinterpret_cast<d2*>(base);
+    s->d.peers.flags[r] = reinterpret_cast<unsigned long long*>((char*)base + s->xch_flag_offset);
+    bool all = true;
+    for (int q = 0; q < s->shard_count; ++q) all = all && s->peer_xch[q] != nullptr;
+    if (all) {
+        s->peer_count = s->shard_count;
+        if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int emme_pic_pweight_sum(const emme_pic_params* p, long n, const double* v_para, const double* v_perp, double* sum) {
+    if (!p) return capi_fail(-1, "null params");
+    if (n < 0) return capi_fail(-2, "negative marker count");
+    if (!v_para || !v_perp) return capi_fail(-3, "null velocity array");
+    if (!sum) return capi_fail(-5, "null output");
+    const double wa = 1 - p->water_bag_weight_vpara, wb = 1 - p->water_bag_weight_vperp;
+    double acc = 0;
+    // the exponent is -0/(2 vt^2) for unit weights: exp gives exactly 1, v_perp * 1 = v_perp
+    if (wa == 0 && wb == 0) for (long i = 0; i < n; ++i) acc += v_perp[i];
+    else for (long i = 0; i < n; ++i) acc += pweight_raw(p, v_para[i], v_perp[i], wa, wb);
+    *sum = acc;
+    return 0;
+}
+
+int emme_pic_create_block(const emme_pic_params* p, long n_total, long first, long n_local, const double* eta,
+                          const double* v_para, const double* v_perp, const double* weight, double pw_sum,
+                          int shard_index, int shard_count, int device, emme_pic** out) {
+    if (!p) return capi_fail(-1, "null params");
+    if (n_total <= 0) return capi_fail(-2, "marker count must be positive");
+    if (first < 0 || n_local < 0 || first + n_local > n_total) return capi_fail(-3, "block outside the marker range");
+    if (!eta || !v_para || !v_perp || !weight) return capi_fail(-5, "null marker array");
+    if (!(pw_sum > 0)) return capi_fail(-9, "the p_weight sum over all markers must be positive");
+    if (shard_count < 1 || shard_count > EMME_MAX_PEER_RANKS || shard_index < 0 || shard_index >= shard_count)
+        return capi_fail(-10, "bad shard");
+    if (!out) return capi_fail(-13, "null output handle");
+    return create_impl(p, n_total, first, n_local, eta, v_para, v_perp, weight, pw_sum, shard_index, shard_count,
+                       device, out);
+}
+
+int emme_pic_create_shard(const emme_pic_params* p, long n_total, const double* eta,
+                          const double* v_para, const double* v_perp, const double* weight,
+                          int shard_index, int shard_count, int device, emme_pic** out) {
+    if (!p) return capi_fail(-1, "null params");
+    if (n_total <= 0) return capi_fail(-2, "marker count must be positive");
+    if (!eta) return capi_fail(-3, "null eta");
+    if (!v_para) return capi_fail(-4, "null v_para");
+    if (!v_perp) return capi_fail(-5, "null v_perp");
+    if (!weight) return capi_fail(-6, "null weight");
+    if (shard_count < 1 || shard_count > EMME_MAX_PEER_RANKS || shard_index < 0 || shard_index >= shard_count)
+        return capi_fail(-7, "bad shard");
+    if (!out) return capi_fail(-10, "null output handle");
+    // initialize_marker_extras (include/solver_pic.h:207-238): p_weight normalised over ALL markers,
+    // summed in the reference's order
+    double sum = 0;
+    if (int rc = emme_pic_pweight_sum(p, n_total, v_para, v_perp, &sum)) return rc;
+    const long per = n_total / shard_count, rem = n_total % shard_count;
+    const long first = shard_index * per + (shard_index < rem ? shard_index : rem);
+    const long n = per + (shard_index < rem ? 1 : 0);
+    return create_impl(p, n_total, first, n, eta + first, v_para + first, v_perp + first, weight + 2 * first, sum,
+                       shard_index, shard_count, device, out);
+}
+
 int emme_pic_create(const emme_pic_params* p, long n_markers, const double* eta, const double* v_para,
                     const double* v_perp, const double* weight, int device, emme_pic** out) {
     return emme_pic_create_shard(p, n_markers, eta, v_para, v_perp, weight, 0, 1, device, out);
+}
+
+// ---- peer mapping of the exchange buffer (CUDA IPC, or plain pointers inside one process) ----
+int emme_pic_ipc_export(emme_pic* s, void* handle64) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (!handle64) return capi_fail(-2, "null output");
+    if (!s->xch) return capi_fail(EMME_E_STATE, "emme_pic_ipc_export: not a sharded state");
+    CU(cudaSetDevice(s->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->xch));
+    std::memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int emme_pic_ipc_import(emme_pic* s, int peer_rank, int peer_count, const void* handle64) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (!s->xch || peer_count != s->shard_count) return capi_fail(-3, "emme_pic_ipc_import: peer count != shard count");
+    if (peer_rank < 0 || peer_rank >= peer_count) return capi_fail(-2, "bad peer rank");
+    CU(cudaSetDevice(s->device));
+    if (peer_rank == s->shard_index) {
+        set_peer(s, peer_rank, s->xch);
+        return 0;
+    }
+    if (!handle64) return capi_fail(-4, "null handle bytes");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_ipc[peer_rank] = true;
+    set_peer(s, peer_rank, ptr);
+    return 0;
+}
+
+int emme_pic_peer_attach(emme_pic* s, int peer_rank, int peer_count, emme_pic* peer) {
+    if (!s) return capi_fail(-1, "null handle");
+    if (!peer || !peer->xch) return capi_fail(-4, "emme_pic_peer_attach: the peer is not a sharded state");
+    if (!s->xch || peer_count != s->shard_count || peer->shard_count != s->shard_count || peer->d.nf != s->d.nf)
+        return capi_fail(-3, "emme_pic_peer_attach: shard count / mesh mismatch");
+    if (peer_rank < 0 || peer_rank >= peer_count) return capi_fail(-2, "bad peer rank");
+    CU(cudaSetDevice(s->device));
+    if (peer->device != s->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, s->device, peer->device));
+        if (!can) return capi_fail(EMME_E_PEER, "emme_pic_peer_attach: no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+    }
+    set_peer(s, peer_rank, peer->xch);
+    return 0;
 }
 
 int emme_pic_destroy(emme_pic* s) {
@@ -761,11 +949,14 @@ int emme_pic_destroy(emme_pic* s) {
     PicDev& d = s->d;
     if (s->stream) {   // back to the pool, stream-ordered
         void* bufs[] = {d.eta, s->d_vpar, s->d_vperp, s->d_pw, d.w, d.A, d.B, d.k1, d.c, d.field, d.dens,
-                        s->d_coef, d.hist, d.part, d.step};
+                        s->d_coef, d.hist, d.part, d.step, s->d_perm};
         for (void* b : bufs)
             if (b) cudaFreeAsync(b, s->stream);
         cudaStreamSynchronize(s->stream);
     }
+    for (int r = 0; r < EMME_MAX_PEER_RANKS; ++r)
+        if (s->peer_xch[r] && s->peer_ipc[r]) cudaIpcCloseMemHandle(s->peer_xch[r]);
+    if (s->xch) cudaFree(s->xch);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -776,9 +967,12 @@ int emme_pic_destroy(emme_pic* s) {
 int emme_pic_step(emme_pic* s, double dt, int nsteps) {
     if (!s) return capi_fail(-1, "null handle");
     if (nsteps < 0) return capi_fail(-3, "negative step count");
-    if (s->shard_count > 1)
-        return capi_fail(EMME_E_STATE, "sharded PIC state: use emme_pic_stage_begin/finish around the density exchange");
+    if (s->shard_count > 1 && s->peer_count != s->shard_count)
+        return capi_fail(EMME_E_STATE, "sharded PIC state without peer mappings: map the ranks (emme_pic_ipc_export/"
+                                       "import or emme_pic_peer_attach), or use emme_pic_stage_begin/finish around "
+                                       "your own density exchange");
     CU(cudaSetDevice(s->device));
+    const int fmode = s->shard_count > 1 ? 3 : 0;   // 3: fused peer exchange inside the field kernel
     if (int rc = ensure_history(s, s->steps_done + nsteps)) return rc;
     if (s->use_persistent && nsteps > 0) {
         const bool sw = s->p.drift_center_transformation_switch != 0;
@@ -804,7 +998,7 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
         cudaError_t e = cudaSuccess;
         for (int st = 0; st < 3 && e == cudaSuccess; ++st) {
             e = launch_stage(s, dt, st);
-            if (e == cudaSuccess) e = launch_field(s, 0, st == 2);
+            if (e == cudaSuccess) e = launch_field(s, fmode, st == 2, st);
         }
         s->launches = before;
         cudaError_t e2 = cudaStreamEndCapture(s->stream, &g);
@@ -822,16 +1016,23 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
         } else {
             for (int st = 0; st < 3; ++st) {
                 CU(launch_stage(s, dt, st));
-                CU(launch_field(s, 0, st == 2));
+                CU(launch_field(s, fmode, st == 2, st));
             }
         }
     }
     CU(cudaEventRecord(s->ev1, s->stream));
+    unsigned long long perr = 0;
+    if (fmode == 3) CU(cudaMemcpyAsync(&perr, s->d.peers.err, sizeof perr, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_ms = ms;
     s->steps_done += nsteps;
+    if (perr != 0) {
+        CU(cudaMemsetAsync(s->d.peers.err, 0, sizeof perr, s->stream));
+        return capi_fail(EMME_E_PEER, "PIC density exchange: a peer did not deliver its density in time (stage serial " +
+                                          std::to_string(perr) + "); the ranks are out of step");
+    }
     return 0;
 }
 
@@ -894,6 +1095,7 @@ int emme_pic_markers(emme_pic* s, double* eta, double* weight) {
     if (eta) CU(cudaMemcpyAsync(t_eta.data(), s->d.eta, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
     if (weight) CU(cudaMemcpyAsync(t_w.data(), s->d.w, sizeof(d2) * s->n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    if (int rc = ensure_perm(s)) return rc;
     for (long j = 0; j < s->n; ++j) {   // back to the caller's marker order
         const long i = s->perm[j];
         if (eta) eta[i] = t_eta[j];
@@ -908,12 +1110,23 @@ int emme_pic_markers(emme_pic* s, double* eta, double* weight) {
 int emme_pic_extras(emme_pic* s, double* omega_dv, double* omega_st, double* p_weight, double* coef) {
     if (!s) return capi_fail(-1, "null handle");
     const emme_pic_params& p = s->p;
-    for (long i = 0; i < s->n; ++i) {
-        const double vp = s->h_vpar[i], vq = s->h_vperp[i];
-        if (omega_dv) omega_dv[i] = (vp * vp + .5 * vq * vq) / (2. * p.vt * p.vt);
-        if (omega_st)
-            omega_st[i] = p.omega_s_i * (1. + p.eta_i * ((vp * vp + vq * vq) / (2. * p.vt * p.vt) - 1.5));
-        if (p_weight) p_weight[i] = s->h_pw[i];
+    if (omega_dv || omega_st || p_weight) {
+        // the marker constants live on the device only (in device order): fetch and un-permute
+        CU(cudaSetDevice(s->device));
+        std::vector<double> t_vpar(s->n), t_vperp(s->n), t_pw(s->n);
+        CU(cudaMemcpyAsync(t_vpar.data(), s->d_vpar, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(t_vperp.data(), s->d_vperp, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(t_pw.data(), s->d_pw, sizeof(double) * s->n, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (int rc = ensure_perm(s)) return rc;
+        for (long j = 0; j < s->n; ++j) {
+            const long i = s->perm[j];
+            const double vp = t_vpar[j], vq = t_vperp[j];
+            if (omega_dv) omega_dv[i] = (vp * vp + .5 * vq * vq) / (2. * p.vt * p.vt);
+            if (omega_st)
+                omega_st[i] = p.omega_s_i * (1. + p.eta_i * ((vp * vp + vq * vq) / (2. * p.vt * p.vt) - 1.5));
+            if (p_weight) p_weight[i] = t_pw[j];
+        }
     }
     if (coef)
         for (int i = 0; i < p.npoints; ++i) coef[i] = s->h_coef[i];

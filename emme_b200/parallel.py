@@ -176,12 +176,18 @@ class _DevVector:
 class ShardedPIC:
     """PIC_State + Integrator with the markers split over the ranks of a process group.
 
-    Every rank passes ALL markers (the p_weight normalisation runs over all of them, in the
-    reference's order) and keeps its block.  step() runs, per stage, the rank's stage kernel, one
-    NCCL all-reduce of the density on the handle's stream, and the field kernel; no host
-    synchronisation inside a step.  Every rank ends with the same field history."""
+    exchange="p2p" (default): the ranks map each other's exchange buffers with CUDA IPC once; from
+    then on step() is the plain emme_pic_step -- the field kernel of every stage stores the rank's
+    density into every peer's buffer over NVLink, signals per 32-cell block with release stores and
+    adds the contributions in rank order (csrc/pic.cu, pic_field_kernel mode 3).  No collective call,
+    no host synchronisation inside a step, every rank ends with the same field history bit for bit.
+    exchange="nccl" is the baseline it replaced: one all-reduce of 2*npoints doubles per stage.
 
-    def __init__(self, params, markers, device=0, group=None):
+    ShardedPIC(params, markers): every rank passes ALL markers (the p_weight normalisation then runs
+    over all of them in the reference's order) and keeps its block.  ShardedPIC.from_seed draws only
+    the rank's own block and reduces the normalisation with one 8-byte all-reduce."""
+
+    def __init__(self, params, markers=None, device=0, group=None, exchange="p2p", _state=None):
         import torch
         import torch.distributed as dist
 
@@ -191,27 +197,56 @@ class ShardedPIC:
         on = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if on else 0
         self.world = dist.get_world_size(group) if on else 1
-        self.state = PIC_State(params, markers=markers, device=device, shard=(self.rank, self.world))
+        self.exchange = exchange if self.world > 1 else "none"
+        self.state = _state or PIC_State(params, markers=markers, device=device, shard=(self.rank, self.world))
         self.nf = self.state.nf
-        if self.world > 1:
+        if self.exchange == "p2p":
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, self.state.ipc_export(), group=group)
+            for r, h in enumerate(everyone):
+                self.state.ipc_import(r, self.world, h)
+            dist.barrier(group=group)                # nobody stores before everyone has mapped
+        elif self.exchange == "nccl":
             self._stream = torch.cuda.ExternalStream(self.state.stream(), device=device)
             self._dens = torch.as_tensor(_DevVector(self.state.density_ptr(), 2 * self.nf),
                                          device=f"cuda:{device}")
 
     @classmethod
-    def from_seed(cls, params, n_markers, seed=1, device=0, group=None):
-        """Load `n_markers` markers with the reference's mt19937 stream (PIC_State::initialize_marker)
-        and keep this rank's block."""
-        from .pic import load_markers
-        return cls(params, load_markers(params, n_markers, seed=seed), device=device, group=group)
+    def from_seed(cls, params, n_markers, seed=1, device=0, group=None, exchange="p2p"):
+        """Rank r draws ITS block of the n_markers markers from its own std::mt19937 stream (seed + r,
+        the reference's distributions and draw order) -- no rank generates or holds another rank's
+        markers -- and the p_weight normalisation (a sum over all markers) is completed with one
+        8-byte all-reduce.  The marker set is therefore not the one a single stream would give; the
+        reference seeds from std::random_device (include/solver_pic.h:356-359), so its own runs
+        differ from each other in the same way."""
+        import torch
+        import torch.distributed as dist
+
+        from .pic import PIC_State, load_markers, pweight_sum
+        on = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank(group) if on else 0
+        world = dist.get_world_size(group) if on else 1
+        first, count = marker_shard(n_markers, rank, world)
+        block = load_markers(params, count, seed=seed + rank)
+        total = pweight_sum(params, block[1], block[2])
+        if world > 1:
+            dev = f"cuda:{device}" if dist.get_backend(group) == "nccl" else "cpu"
+            t = torch.tensor([total], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            total = float(t.item())
+        state = PIC_State.from_block(params, n_markers, first, block, total, (rank, world), device=device)
+        return cls(params, device=device, group=group, exchange=exchange, _state=state)
 
     def exchange_description(self):
-        return "one NCCL all-reduce (sum) of 2*npoints doubles per stage on the handle's stream"
+        if self.exchange == "nccl":
+            return "one NCCL all-reduce (sum) of 2*npoints doubles per stage on the handle's stream"
+        return ("fused into the field kernel: per-stage density stored into every peer's buffer over NVLink "
+                "(CUDA IPC), release/acquire flags per 32-cell block, fixed-order sum; no collective call")
 
     def step(self, dt, nsteps=1):
         import torch
         import torch.distributed as dist
-        if self.world == 1:
+        if self.exchange != "nccl":
             self.state.step(dt, nsteps)
             return
         with torch.cuda.stream(self._stream):      # collectives are ordered after the stage kernels
@@ -236,7 +271,46 @@ class ShardedPIC:
         return self.state.markers()
 
     def close(self):
+        import torch.distributed as dist
+        if self.exchange == "p2p" and dist.is_initialized() and getattr(self.state, "_h", None):
+            self.synchronize()
+            dist.barrier(group=self._group)          # peers may still be storing into my buffer
         self.state.close()
+
+
+class LocalShardedPIC:
+    """ShardedPIC's p2p protocol inside ONE process: `world` states (rank r on devices[r], several
+    ranks per device allowed) attached with emme_pic_peer_attach, one host thread per rank."""
+
+    def __init__(self, params, markers, devices):
+        from .pic import PIC_State
+        self.world = len(devices)
+        self.ranks = [PIC_State(params, markers=markers, device=d, shard=(r, self.world))
+                      for r, d in enumerate(devices)]
+        for s in self.ranks:
+            for q, peer in enumerate(self.ranks):
+                s.peer_attach(q, self.world, peer)
+
+    def step(self, dt, nsteps=1):
+        import threading
+        errs = []
+
+        def run(s):
+            try:
+                s.step(dt, nsteps)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=run, args=(s,)) for s in self.ranks]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def close(self):
+        for s in self.ranks:
+            s.close()
 
 
 class _DevMatrix:

@@ -37,6 +37,14 @@ def load_markers(params, n, seed=-1):
     return eta, v_para, v_perp, weight
 
 
+def pweight_sum(params, v_para, v_perp):
+    """Sum of the un-normalised p_weight (include/solver_pic.h:229-232) over the given markers."""
+    v_para, v_perp = (np.ascontiguousarray(a, dtype=np.float64) for a in (v_para, v_perp))
+    out = C.c_double()
+    capi.check(capi.load().emme_pic_pweight_sum(C.byref(params), v_para.shape[0], _dp(v_para), _dp(v_perp), C.byref(out)))
+    return out.value
+
+
 def calculate_omega(stats, dt):
     """util::calculate_omega: stats is (steps, 3) = mean Re, mean Im, rms of the field per step."""
     stats = np.ascontiguousarray(stats, dtype=np.float64)
@@ -70,6 +78,35 @@ class PIC_State:
     @classmethod
     def from_markers(cls, params, eta, v_para, v_perp, weight, device=0, shard=(0, 1)):
         return cls(params, markers=(eta, v_para, v_perp, weight), device=device, shard=shard)
+
+    @classmethod
+    def from_block(cls, params, n_total, first, block, pw_sum, shard, device=0):
+        """This rank's contiguous block [first, first + len) of n_total markers; pw_sum is the
+        un-normalised p_weight summed over ALL markers (pweight_sum per block, added over ranks)."""
+        self = cls.__new__(cls)
+        self._lib = capi.load()
+        self.params = params
+        eta, v_para, v_perp, weight = (np.ascontiguousarray(a) for a in block)
+        weight = weight.astype(np.complex128, copy=False)
+        self.n_total = int(n_total)
+        self._h = C.c_void_p()
+        capi.check(self._lib.emme_pic_create_block(C.byref(params), self.n_total, int(first), eta.shape[0], _dp(eta),
+                                                    _dp(v_para), _dp(v_perp), _dp(weight.view(np.float64)),
+                                                    float(pw_sum), shard[0], shard[1], device, C.byref(self._h)))
+        self.nf = params.npoints
+        return self
+
+    # peer mapping of the density exchange buffer (multi-GPU without a collective library)
+    def ipc_export(self):
+        buf = C.create_string_buffer(64)
+        capi.check(self._lib.emme_pic_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_import(self, peer_rank, peer_count, handle):
+        capi.check(self._lib.emme_pic_ipc_import(self._h, peer_rank, peer_count, C.create_string_buffer(handle, 64)))
+
+    def peer_attach(self, peer_rank, peer_count, peer):
+        capi.check(self._lib.emme_pic_peer_attach(self._h, peer_rank, peer_count, peer._h))
 
     @classmethod
     def from_input(cls, inp, seed=-1, device=0):

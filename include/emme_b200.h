@@ -275,6 +275,23 @@ void* emme_pic_stream(emme_pic* s);
 int emme_pic_create_shard(const emme_pic_params* p, long n_markers, const double* eta,
                           const double* v_para, const double* v_perp, const double* weight,
                           int shard_index, int shard_count, int device, emme_pic** out);
+/* The same for callers that hold only their own block: first = index of the block's first marker in
+ * the global order, the four arrays are the BLOCK (n_local markers), pw_sum = sum over ALL markers of
+ * the un-normalised p_weight (emme_pic_pweight_sum per block, added over the ranks by the caller:
+ * one 8-byte reduction instead of every rank holding every marker). */
+int emme_pic_pweight_sum(const emme_pic_params* p, long n, const double* v_para, const double* v_perp, double* sum);
+int emme_pic_create_block(const emme_pic_params* p, long n_total, long first, long n_local, const double* eta,
+                          const double* v_para, const double* v_perp, const double* weight, double pw_sum,
+                          int shard_index, int shard_count, int device, emme_pic** out);
+/* Fused density exchange (no collective library): every rank exports the CUDA IPC handle (64 bytes) of
+ * its exchange buffer and imports every peer's (own rank included, any bytes); from then on
+ * emme_pic_step works on sharded states -- the field kernel of every stage stores the rank's density
+ * into every peer's buffer over NVLink, signals per 32-cell block and adds the P contributions in rank
+ * order, so every rank holds the same field, bit for bit.  emme_pic_peer_attach: the same for states
+ * inside one process.  A peer that does not arrive within 20 s fails the call with EMME_E_PEER. */
+int emme_pic_ipc_export(emme_pic* s, void* handle64);
+int emme_pic_ipc_import(emme_pic* s, int peer_rank, int peer_count, const void* handle64);
+int emme_pic_peer_attach(emme_pic* s, int peer_rank, int peer_count, emme_pic* peer);
 int emme_pic_stage_begin(emme_pic* s, double dt, int stage);
 int emme_pic_stage_finish(emme_pic* s, int stage);
 void* emme_pic_density_ptr(emme_pic* s);

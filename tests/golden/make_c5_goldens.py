@@ -37,7 +37,11 @@ def main():
                 rec = {"k_rho": k_rho, "omega0": [w0.real, w0.imag], "iterates": r["iterates"],
                        "final": r["final"], "times": r["times"]}
             except Exception as e:  # noqa: BLE001 - the reference's failure IS the golden
-                rec = {"k_rho": k_rho, "omega0": [w0.real, w0.imag], "error": (getattr(e, "stdout", "") or str(e))[-600:]}
+                lines = (getattr(e, "stdout", "") or str(e)).splitlines()
+                rec = {"k_rho": k_rho, "omega0": [w0.real, w0.imag],
+                       "iterates": [[float(x) for x in ln.split()[2:6]] for ln in lines if ln.startswith("ITER")],
+                       "error": next((ln[6:] for ln in lines if ln.startswith("ERROR")), "\n".join(lines)[-300:]),
+                       "note": "the reference's scan records this point as {\"eigenvalue\": \"NaN\"} (src/main.cpp:311-318)"}
             G["points"][str(k)] = rec
             print(k, rec.get("final"), rec.get("error"), flush=True)
             out_path.write_text(json.dumps(G, indent=1))

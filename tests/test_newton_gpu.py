@@ -458,13 +458,13 @@ def test_blocked_symmetric_path_independent_of_outer_block(dim, native_lib, monk
     _trace_solver(4).close()                 # restore the default outer block (process-wide setting)
 
 
-@pytest.mark.parametrize("k", [9, 27, 63])
+@pytest.mark.parametrize("k", [0, 9, 27, 54, 63])
 def test_c5_points_match_reference(k, native_lib):
     """BASELINE configs[4] (64 independent wavenumbers, N=1024): the iterate lists of the unmodified
-    reference for three of the points (tests/golden/c5.json from make_c5_goldens.py) -- a
-    10-iterate wandering trajectory (k=9), the 4-iterate neighbour of C1 (k=27), and a point on
-    which the reference itself fails at iterate 3 with "Linear solve failed" (k=63), which the
-    scan records as NaN (src/main.cpp:311-318)."""
+    reference for five of the points (tests/golden/c5.json from make_c5_goldens.py) -- a point that
+    uses all 21 iterates without converging (k=0), a 10-iterate wandering trajectory (k=9), the
+    4-iterate neighbour of C1 (k=27), and two points on which the reference itself fails at iterate 3
+    with "Linear solve failed" (k=54, 63), which the scan records as NaN (src/main.cpp:311-318)."""
     import json
     from emme_b200 import EmmeError, workloads
     gold = json.loads((cases.GOLD / "c5.json").read_text())["points"][str(k)]
@@ -492,7 +492,9 @@ def test_c5_points_match_reference(k, native_lib):
         # last iterate holds NaN entries (overflow of the reference's Bessel recurrence, reproduced)
         A = s.eigen_matrix
         nan_at = sorted(map(tuple, np.argwhere(np.isnan(A)).tolist()))
-        assert nan_at == [(132, 842), (181, 891), (842, 132), (891, 181)], nan_at
+        assert len(nan_at) >= 2 and all((j, i) in nan_at for i, j in nan_at), nan_at
+        if k == 63:      # the pairs found by assembling with the reference itself
+            assert nan_at == [(132, 842), (181, 891), (842, 132), (891, 181)], nan_at
         with pytest.raises(EmmeError) as ei:
             s.newtonTraceSecantIteration()
         assert "Linear solve failed" in str(ei.value)

@@ -251,3 +251,55 @@ def test_host_program_pic_end_to_end(tmp_path, native_lib, monkeypatch):
     assert '"scan_key": "(None)"' in out and '"eigenvector"' in out
     # run-to-run: deposits are summed in a varying order, so only to rounding
     assert np.abs(F[-1] - res["eigenvector"]).max() <= 1e-9 * np.abs(F[-1]).max()
+
+
+@pytest.mark.parametrize("world,case", [(2, "n32"), (3, "n64_wb"), (4, "n32_noswitch")])
+def test_sharded_markers_fused_exchange_one_device(world, case, native_lib, monkeypatch):
+    """The multi-GPU PIC protocol on ONE device (several ranks, one host thread each): markers in
+    contiguous blocks, the field kernel of every stage stores the rank's density into every peer's
+    exchange buffer, signals per 32-cell block and adds the contributions in rank order.  Every rank
+    must hold the SAME field history bit for bit; against the single-state run the fields agree to
+    rounding (the deposit order differs) and the positions exactly."""
+    from emme_b200 import parallel
+    # plain launches: a CUDA-graph launch of one rank does not start while other ranks' device-side
+    # waits are resident on the SAME device (several ranks per GPU only; see test_sharded_gpu.py)
+    monkeypatch.setenv("EMME_PIC_GRAPH", "0")
+    native_lib.emme_peer_set_timeout(4.0)
+    g, p, _, dt = load_case(case)
+    steps = int(g["steps"])
+    markers = (g["eta"], g["v_para"], g["v_perp"], g["weight"])
+    grp = parallel.LocalShardedPIC(p, markers, devices=[0] * world)
+    grp.step(dt, 2)
+    grp.step(dt, steps - 2)
+    hists = [s.field_history() for s in grp.ranks]
+    for h in hists[1:]:
+        assert np.array_equal(h, hists[0])
+    for t in range(steps):
+        ref = g["fields"][t]
+        assert np.abs(hists[0][t] - ref).max() / np.abs(ref).max() <= FIELD_TOL, t
+    n = g["eta"].shape[0]
+    eta_all = np.concatenate([s.markers()[0] for s in grp.ranks])
+    assert eta_all.shape[0] == n and np.array_equal(eta_all, g["eta_final"])
+    pw_all = np.concatenate([s.extras()[2] for s in grp.ranks])
+    assert np.array_equal(pw_all, g["p_weight"])
+    grp.close()
+    native_lib.emme_peer_set_timeout(20.0)
+
+
+def test_block_creation_matches_full_marker_creation(native_lib):
+    """emme_pic_create_block (a rank passes only ITS markers + the global p_weight sum) builds the
+    same state as emme_pic_create_shard (every rank passes all markers)."""
+    g, p, _, dt = load_case("n64_wb")
+    markers = (g["eta"], g["v_para"], g["v_perp"], g["weight"])
+    n = g["eta"].shape[0]
+    total = pic.pweight_sum(p, g["v_para"], g["v_perp"])
+    first, count = n // 3, n - n // 3 - 7
+    blk = tuple(a[first:first + count] for a in markers)
+    a = pic.PIC_State.from_block(p, n, first, blk, total, (0, 1))
+    full = pic.PIC_State.from_markers(p, *markers)
+    assert np.array_equal(a.extras()[2], full.extras()[2][first:first + count])
+    assert a.marker_num() == count
+    a.step(dt, 2)      # a lone block is a valid (smaller) state
+    assert np.isfinite(a.current_field()).all()
+    a.close()
+    full.close()
