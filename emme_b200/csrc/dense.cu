@@ -710,6 +710,20 @@ __device__ __forceinline__ z_t zrecip_fast(z_t a) {
     return zrecip(a);
 }
 
+// 1/u of a pivot: hardware seed + two Newton steps on |u|^2 (<= 1 ulp; the special cases of the
+// library division cannot occur for an accepted pivot).  ONE definition: the panel kernel and the
+// ranks that rebuild a received panel (lpanel_from_u12_kernel) must form bit-identical multipliers.
+__device__ __forceinline__ z_t pivot_recip(z_t u, double& n2) {
+    n2 = fma(u.x, u.x, u.y * u.y);
+    double d;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(d) : "d"(n2));
+    double er = fma(-n2, d, 1.0);
+    d = fma(d, er, d);
+    er = fma(-n2, d, 1.0);
+    d = fma(d, er, d);
+    return make_double2(u.x * d, -u.y * d);
+}
+
 // One launch per NB-wide panel [k0, k0+jb).  Small code, no per-thread register rows (the
 // unrolled one-thread-per-row elimination of panel_nopiv_kernel is instruction-fetch bound: every
 // instruction executes once), tensor cores for the two block products:
@@ -815,16 +829,10 @@ panel_sym_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, int ld, int dim, int 
                 }
             // 1/u: hardware seed + two Newton steps; a zero, non-finite or badly scaled pivot is
             // reported through the flag (integer test on the exponent field)
-            const double n2 = u.x * u.x + u.y * u.y;
+            double n2;
+            const z_t inv = pivot_recip(u, n2);
             const unsigned ex = ((unsigned)__double2hiint(n2) >> 20) & 0x7ffu;
             if (ex < 64u || ex > 1983u) bad = 1;
-            double d;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(d) : "d"(n2));
-            double er = fma(-n2, d, 1.0);
-            d = fma(d, er, d);
-            er = fma(-n2, d, 1.0);
-            d = fma(d, er, d);
-            const z_t inv = make_double2(u.x * d, -u.y * d);
             const double ua = fabs(u.x) + fabs(u.y);
             if (tid == 0) {
                 sInv[c] = inv;
@@ -1451,41 +1459,65 @@ struct ShardPtrs {
     int n, me;
 };
 
-// Copy panel K to every other rank: W[KE:dim, K0:KE) (L panel below the diagonal block),
-// W[K0:KE, KE:dim) (U12), Y[K0:KE, K0:KE) (M_KK) and the pivots d[K0:KE).  Row-contiguous 16-byte accesses.
+// Copy panel K to the ranks in `mask`: the mirrored block row U12 = W[K0:KE, KE:dim) (= T^T, the
+// entries of the panel just before their column was eliminated), M_KK = Y[K0:KE, K0:KE) and the
+// pivots d[K0:KE).  The L panel itself is NOT sent: every receiver rebuilds it from U12 and the
+// pivots with the owner's own operation (lpanel_from_u12_kernel), which halves the NVLink volume.
+// Row-contiguous 16-byte accesses.
 __global__ void __launch_bounds__(256)
-publish_panel_kernel(const ShardPtrs sp, int ld, int dim, int K0, int JB) {
+publish_panel_kernel(const ShardPtrs sp, int ld, int dim, int K0, int JB, unsigned mask) {
     const int KE = K0 + JB;
-    const size_t n1 = (size_t)(dim - KE) * JB;          // L panel
     const size_t n2 = (size_t)JB * (dim - KE);          // U12
     const size_t n3 = (size_t)JB * JB;                  // M_KK
-    const size_t total = n1 + n2 + n3;
+    const size_t total = n2 + n3;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid < (size_t)JB) {
         const z_t v = sp.dvec[sp.me][K0 + gid];
 #pragma unroll
         for (int r = 0; r < EMME_MAX_PEERS; ++r)
-            if (r < sp.n && r != sp.me) sp.dvec[r][K0 + gid] = v;
+            if (r < sp.n && r != sp.me && ((mask >> r) & 1u)) sp.dvec[r][K0 + gid] = v;
     }
     for (size_t e = gid; e < total; e += stride) {
         size_t off;
         bool in_y = false;
-        if (e < n1) {
-            off = (size_t)(KE + e / JB) * ld + K0 + e % JB;
-        } else if (e < n1 + n2) {
-            const size_t f = e - n1;
+        if (e < n2) {
             const int w = dim - KE;
-            off = (size_t)(K0 + f / w) * ld + KE + f % w;
+            off = (size_t)(K0 + e / w) * ld + KE + e % w;
         } else {
-            const size_t f = e - n1 - n2;
+            const size_t f = e - n2;
             off = (size_t)(K0 + f / JB) * ld + K0 + f % JB;
             in_y = true;
         }
         const z_t v = in_y ? sp.Y[sp.me][off] : sp.W[sp.me][off];
 #pragma unroll
         for (int r = 0; r < EMME_MAX_PEERS; ++r)
-            if (r < sp.n && r != sp.me) (in_y ? sp.Y[r] : sp.W[r])[off] = v;
+            if (r < sp.n && r != sp.me && ((mask >> r) & 1u)) (in_y ? sp.Y[r] : sp.W[r])[off] = v;
+    }
+}
+
+// Receiver side: L[KE + r][K0 + c] = U12[K0 + c][KE + r] * (1/d_c) -- the very product the owner's
+// panel kernel formed (same t, same pivot_recip), so the rebuilt panel is bit-identical to the
+// owner's.  32 x 32 tiles through shared memory, block (32, 8).
+__global__ void __launch_bounds__(256)
+lpanel_from_u12_kernel(z_t* __restrict__ W, const z_t* __restrict__ dvec, int ld, int dim, int K0, int JB) {
+    __shared__ z_t t[32][33];
+    __shared__ z_t sinv[32];
+    const int KE = K0 + JB;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    if (threadIdx.y == 0) {
+        double n2;
+        const int c = c0 + threadIdx.x;
+        sinv[threadIdx.x] = c < JB ? pivot_recip(dvec[K0 + c], n2) : make_double2(0., 0.);
+    }
+    for (int cc = threadIdx.y; cc < 32; cc += 8) {
+        const int c = c0 + cc, r = r0 + threadIdx.x;
+        t[cc][threadIdx.x] = (c < JB && KE + r < dim) ? W[(size_t)(K0 + c) * ld + KE + r] : make_double2(0., 0.);
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+        const int r = r0 + rr, c = c0 + threadIdx.x;
+        if (c < JB && KE + r < dim) W[(size_t)(KE + r) * ld + K0 + c] = zmul(t[threadIdx.x][rr], sinv[threadIdx.x]);
     }
 }
 
@@ -1693,12 +1725,24 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                 if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, K0, ke - K0, k0, jb);
             }
             if (P > 1) {
-                const size_t total = 2 * (size_t)(dim - KE) * JB + (size_t)JB * JB;
+                // the owner of the NEXT panel is on the critical path (it must update its block with
+                // this panel and factor it): it is served and signalled first, the others follow
+                const size_t total = (size_t)(dim - KE) * JB + (size_t)JB * JB;
                 int blocks = (int)((total + 1023) / 1024);
                 if (blocks > 1184) blocks = 1184;
-                publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB);
-                DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, stream));
-                nl += 2;
+                const unsigned all = (P >= 32 ? 0xffffffffu : ((1u << P) - 1u)) & ~(1u << me);
+                const int next = (K + 1 < nb) ? owner(K + 1) : -1;
+                unsigned first = (next >= 0 && next != me) ? (1u << next) : 0u;
+                if (first) {
+                    publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB, first);
+                    DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, stream, first));
+                    nl += 2;
+                }
+                if (all & ~first) {
+                    publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB, all & ~first);
+                    DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, stream, all & ~first));
+                    nl += 2;
+                }
             }
             return cudaGetLastError();
         };
@@ -1724,6 +1768,18 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
             if (owner(K) != me) {
                 DCHK(launch_peer_wait(peers->flags, PEER_W_PANEL + K, peers->serial, stream));
                 ++nl;
+                if (KE < dim) {   // rebuild the L panel from the received U12 and pivots
+                    lpanel_from_u12_kernel<<<dim3((JB + 31) / 32, (dim - KE + 31) / 32), dim3(32, 8), 0, stream>>>(
+                        W, dvec, ld, dim, K0, JB);
+                    ++nl;
+                }
+            }
+            // look-ahead first (the critical path of the whole step runs through the panels): the
+            // owner of panel K+1 brings that block up to date, factors and publishes it
+            const bool ahead = KE < dim && K + 1 < nb && owner(K + 1) == me;
+            if (ahead) {
+                shard_update(K0, JB, K + 1, K + 2, 0, 0);
+                DCHK(factor_publish(K + 1));
             }
             // rows K of my columns of Y become final: Y_K <- M_KK Y_K (blocks < K), via the scratch S
             const int y0 = first_own(0);
@@ -1741,15 +1797,8 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                                        cudaMemcpyDeviceToDevice, stream));
             }
             if (KE >= dim) continue;
-            const int w0 = first_own(K + 1);
-            if (K + 1 < nb && owner(K + 1) == me) {
-                // look-ahead: bring block K+1 up to date, factor and publish it, then the rest
-                shard_update(K0, JB, K + 1, K + 2, 0, 0);
-                DCHK(factor_publish(K + 1));
-                shard_update(K0, JB, K + 1 + P, nb, y0, K + 1);
-            } else {
-                shard_update(K0, JB, w0, nb, y0, K + 1);
-            }
+            if (ahead) shard_update(K0, JB, K + 1 + P, nb, y0, K + 1);
+            else shard_update(K0, JB, first_own(K + 1), nb, y0, K + 1);
         }
         if (P > 1) {
             // every rank's final rows of Y have arrived everywhere
@@ -1819,6 +1868,7 @@ cudaError_t dense_preload() {
     EMME_TOUCH(secant_kernel);
     EMME_TOUCH(conj_normalise_kernel);
     EMME_TOUCH(publish_panel_kernel);
+    EMME_TOUCH(lpanel_from_u12_kernel);
     EMME_TOUCH(ydiag_kernel);
     EMME_TOUCH(ycopy_kernel);
     EMME_TOUCH(shard_update_kernel);

@@ -22,9 +22,9 @@ peer_barrier_kernel(const PeerFlags f, unsigned long long epoch, unsigned long l
 }
 
 __global__ void __launch_bounds__(32)
-peer_signal_kernel(const PeerFlags f, int word, unsigned long long value) {
+peer_signal_kernel(const PeerFlags f, int word, unsigned long long value, unsigned mask) {
     const int r = threadIdx.x;
-    if (r >= f.n || r == f.me) return;
+    if (r >= f.n || r == f.me || !((mask >> r) & 1u)) return;
     __threadfence_system();
     st_release_sys(f.p[r] + word, value);
 }
@@ -77,8 +77,9 @@ cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned long long epoch, cu
     peer_barrier_kernel<<<1, 32, 0, stream>>>(f, epoch, g_timeout_ns);
     return cudaGetLastError();
 }
-cudaError_t launch_peer_signal(const PeerFlags& f, int word, unsigned long long value, cudaStream_t stream) {
-    peer_signal_kernel<<<1, 32, 0, stream>>>(f, word, value);
+cudaError_t launch_peer_signal(const PeerFlags& f, int word, unsigned long long value, cudaStream_t stream,
+                               unsigned mask) {
+    peer_signal_kernel<<<1, 32, 0, stream>>>(f, word, value, mask);
     return cudaGetLastError();
 }
 cudaError_t launch_peer_wait(const PeerFlags& f, int word, unsigned long long value, cudaStream_t stream) {

@@ -30,8 +30,10 @@ struct PeerFlags {
 
 // all ranks arrive at `epoch` (every rank passes the same, increasing epoch): 1 CTA, 32 threads
 cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned long long epoch, cudaStream_t stream);
-// store `value` into word `word` of every OTHER rank's page (ordered after this stream's earlier kernels)
-cudaError_t launch_peer_signal(const PeerFlags& f, int word, unsigned long long value, cudaStream_t stream);
+// store `value` into word `word` of the page of every OTHER rank in `mask` (bit r = rank r; ordered
+// after this stream's earlier kernels)
+cudaError_t launch_peer_signal(const PeerFlags& f, int word, unsigned long long value, cudaStream_t stream,
+                               unsigned mask = 0xffffffffu);
 // block the stream until word `word` of the local page is >= value (bounded: sets PEER_W_ERROR on timeout)
 cudaError_t launch_peer_wait(const PeerFlags& f, int word, unsigned long long value, cudaStream_t stream);
 // mailbox: {serial, a, b, c} into slot `me` of EVERY rank's page (own included)
