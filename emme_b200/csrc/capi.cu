@@ -46,6 +46,11 @@ struct emme_solver {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evd0 = nullptr, evd1 = nullptr;   // dense-step timing (created once, not per step)
+    emme::DenseAux aux{};             // side stream + events of the dense step's look-ahead
+    // EMME_DENSE_LOOKAHEAD=1: split the rank-32 update of the single-level path over two streams so
+    // that the next panel starts early.  Bitwise neutral (tests), measured neutral in time as well
+    // (dim 2048: 3.23 vs 3.23 ms, with and without stream priorities): off by default.
+    int use_lookahead = 0;
     // emme_copy_matrix_async: device->host copies overlap the next iterate on their own stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_src = nullptr, ev_copy_done = nullptr;
@@ -59,6 +64,7 @@ struct emme_solver {
     void* d_spill = nullptr;
     void* d_trig = nullptr;           // node table of kernel 1
     int spill_cap = 0, grid_blocks = 0;
+    int launch_blocks = 0;            // CTAs actually launched (<= grid_blocks, which sizes the spill area)
     void* d_dense_ws = nullptr;
     // symmetric dense path: M = L^-1, its scaled transpose, per-tile partial traces
     void *Y = nullptr, *YT = nullptr, *d_sym_ws = nullptr;
@@ -186,6 +192,9 @@ int emme_destroy(emme_solver* s) {
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->evd0) cudaEventDestroy(s->evd0);
     if (s->evd1) cudaEventDestroy(s->evd1);
+    if (s->aux.ev_panel) cudaEventDestroy(s->aux.ev_panel);
+    if (s->aux.ev_rest) cudaEventDestroy(s->aux.ev_rest);
+    if (s->aux.side) cudaStreamDestroy(s->aux.side);
     if (s->ev_copy_src) cudaEventDestroy(s->ev_copy_src);
     if (s->ev_copy_done) cudaEventDestroy(s->ev_copy_done);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -214,11 +223,21 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     s->N = npoints;
     s->dim = std::fpclassify(p->beta_e) == FP_ZERO ? npoints : 2 * npoints;
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    {
+        // the handle's stream carries the dependent chain of the dense step (panels); the side stream
+        // of the look-ahead carries bulk updates that must yield SM slots to it
+        int prio_low = 0, prio_high = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        CU(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_high));
+        CU(cudaStreamCreateWithPriority(&s->aux.side, cudaStreamNonBlocking, prio_low));
+    }
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     CU(cudaEventCreate(&s->evd0));
     CU(cudaEventCreate(&s->evd1));
+    CU(cudaEventCreateWithFlags(&s->aux.ev_panel, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->aux.ev_rest, cudaEventDisableTiming));
+    if (const char* e = std::getenv("EMME_DENSE_LOOKAHEAD")) s->use_lookahead = std::atoi(e) != 0;
     const size_t tb = sizeof(double) * npoints;
     CU(cudaMalloc(&s->d_eta, tb));
     CU(cudaMalloc(&s->d_g, tb));
@@ -230,6 +249,11 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_stats, 8 * sizeof(unsigned long long)));
     s->grid_blocks = emme::assembly_grid_blocks(p->integration_start_points, device);
+    s->launch_blocks = s->grid_blocks;
+    if (const char* e = std::getenv("EMME_ASM_BLOCKS_PER_SM")) {   // tuning: resident CTAs per SM
+        const int v = std::atoi(e) * s->sms;
+        if (v >= 1 && v <= s->grid_blocks) s->launch_blocks = v;
+    }
     // interval stack: at most integration_iteration_limit right siblings
     if (const char* e = std::getenv("EMME_REFILL_MIN")) s->refill_min = std::atoi(e);
     if (const char* e = std::getenv("EMME_DENSE_GRID_PANEL")) emme::dense_force_grid_panel(std::atoi(e) != 0);
@@ -326,7 +350,7 @@ static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, in
     }
     CU(cudaEventRecord(s->ev0, s->stream));
     CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, ps, shard_index, shard_count,
-                             s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->grid_blocks,
+                             s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->launch_blocks,
                              s->stream, &s->launches, s->refill_min, s->d_trig));
     CU(cudaEventRecord(s->ev1, s->stream));
     return 0;
@@ -446,7 +470,8 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
             } else {
                 int rc = replay_graph(s, &s->sym_graph, &s->sym_graph_launches, [&](unsigned long long* nl) {
                     return emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace,
-                                                  s->d_info, s->d_flag, s->stream, nl);
+                                                  s->d_info, s->d_flag, s->stream, nl, nullptr,
+                                                  s->use_lookahead ? &s->aux : nullptr);
                 });
                 if (rc) return rc;
             }

@@ -1634,7 +1634,7 @@ int dense_sym_outer_block(int dim) { return g_nbo > 0 ? g_nbo : (dim <= 2048 ? N
 // the step; *peers->epoch and peers->serial drive the barriers and panel flags.
 cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int dim, void* sym_workspace,
                              void* d_trace, int* d_info, int* d_flag, cudaStream_t stream,
-                             unsigned long long* n_launches, const DensePeers* peers) {
+                             unsigned long long* n_launches, const DensePeers* peers, const DenseAux* aux) {
     unsigned long long nl = 0;
     z_t* W = (z_t*)Wv;
     z_t* Y = (z_t*)Yv;
@@ -1654,16 +1654,21 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
     // tile = rows (columns of Y) per CTA: small systems get small tiles (more SMs share the products)
     const int tile = dim <= 4736 ? 16 : (dim <= 9472 ? 32 : 64);
     // C1 = W[r1:, c1:c1+N1) (lower block triangle), C2 = Y[r1:r1+M2, yc:yc+N2), A = W[r1:, kb:kb+K)
-    auto update = [&](int r1, int M1, int c1, int N1, int M2, int yc, int N2, int kb, int K) {
+    // C1 = W[r1:r1+M1, c1:c1+N1) (lower block triangle), C2 = Y[r1:r1+M2, yc:yc+N2), A = W[r1:, kb:kb+K),
+    // on stream `st`; returns whether anything was launched
+    auto update_on = [&](cudaStream_t st, int r1, int M1, int c1, int N1, int M2, int yc, int N2, int kb, int K) -> bool {
         const int M = M1 > M2 ? M1 : M2;
-        if (M <= 0) return;
+        if (M <= 0) return false;
         const int nx1 = M1 > 0 ? (N1 + GN - 1) / GN : 0, nx2 = M2 > 0 ? (N2 + GN - 1) / GN : 0;
-        if (nx1 + nx2 == 0) return;
+        if (nx1 + nx2 == 0) return false;
         dim3 g(nx1 + nx2, (M + GM - 1) / GM);
-        zgemm_sym2_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(at(W, r1, c1), at(W, kb, c1), M1, N1, nx1,
-                                                            at(Y, r1, yc), at(Y, kb, yc), M2, N2, ld,
-                                                            at(W, r1, kb), K);
+        zgemm_sym2_kernel<<<g, 256, G_SMEM_BYTES, st>>>(at(W, r1, c1), at(W, kb, c1), M1, N1, nx1, at(Y, r1, yc),
+                                                        at(Y, kb, yc), M2, N2, ld, at(W, r1, kb), K);
         ++nl;
+        return true;
+    };
+    auto update = [&](int r1, int M1, int c1, int N1, int M2, int yc, int N2, int kb, int K) {
+        update_on(stream, r1, M1, c1, N1, M2, yc, N2, kb, K);
     };
     ShardPtrs sp{};
     PartialDst pd{};
@@ -1680,6 +1685,38 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
     if (NBO % GN != 0 || NBO == NB) {
         // ---- single level / unaligned outer block: one GPU only (small systems, launch bound) ----
         if (P > 1) return cudaErrorInvalidValue;
+        if (NBO == NB && aux && aux->side && dim > 2 * NB) {
+            // Single level with LOOK-AHEAD (small systems are bound by the panel chain: 2 dim/32
+            // dependent launches).  The rank-32 update of panel k is split into (a) what panel k+1
+            // reads -- its 32 columns of W and its 32 rows of Y -- on the main stream, followed at once
+            // by panel k+1, and (b) the rest, on a side stream, concurrent with (a) and panel k+1;
+            // (a) of the next step waits for (b).  Every entry sees the same products in the same
+            // order as without the split.  Captured into the step's CUDA graph as fork/join edges.
+            bool side_busy = false;
+            for (int k0 = 0; k0 < dim; k0 += NB) {
+                const int jb = dim - k0 < NB ? dim - k0 : NB;
+                const int ke = k0 + jb;
+                const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
+                panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, 0, ke, n_row,
+                                                                                tile, g_tau, d_flag, dvec);
+                ++nl;
+                if (ke >= dim) break;
+                const int nn = dim - ke < NB ? dim - ke : NB;       // width of the next panel
+                // (b): W[ke+nn:, ke+nn:) lower block triangle and Y[ke+nn:, 0:ke)
+                DCHK(cudaEventRecord(aux->ev_panel, stream));
+                DCHK(cudaStreamWaitEvent(aux->side, aux->ev_panel, 0));
+                const bool has_b = update_on(aux->side, ke + nn, dim - ke - nn, ke + nn, dim - ke - nn, dim - ke - nn,
+                                             0, ke, k0, jb);
+                // (a): W[ke:, ke:ke+nn) and Y[ke:ke+nn, 0:ke) -- after (b) of the previous panel
+                if (side_busy) DCHK(cudaStreamWaitEvent(stream, aux->ev_rest, 0));
+                update_on(stream, ke, dim - ke, ke, nn, nn, 0, ke, k0, jb);
+                if (has_b) {
+                    DCHK(cudaEventRecord(aux->ev_rest, aux->side));
+                    side_busy = true;
+                }
+            }
+            if (side_busy) DCHK(cudaStreamWaitEvent(stream, aux->ev_rest, 0));   // join
+        } else
         for (int K0 = 0; K0 < dim; K0 += NBO) {
             const int JB = dim - K0 < NBO ? dim - K0 : NBO;
             const int KE = K0 + JB;

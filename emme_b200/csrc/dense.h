@@ -44,9 +44,15 @@ struct DensePeers {
     unsigned long long serial;
     unsigned long long* epoch;
 };
+// a side stream and two events (owned by the handle) for the look-ahead of the single-level path
+struct DenseAux {
+    cudaStream_t side;
+    cudaEvent_t ev_panel, ev_rest;
+};
 cudaError_t launch_trace_sym(void* W, void* Y, void* YT, const void* B, int dim, void* sym_workspace,
                              void* d_trace, int* d_info, int* d_flag, cudaStream_t stream,
-                             unsigned long long* n_launches, const DensePeers* peers = nullptr);
+                             unsigned long long* n_launches, const DensePeers* peers = nullptr,
+                             const DenseAux* aux = nullptr);
 // outer block width the symmetric path uses for this size (NB = single level)
 int dense_sym_outer_block(int dim);
 void dense_set_pivot_threshold(double tau);

@@ -506,3 +506,21 @@ def test_c5_points_match_reference(k, native_lib):
 def parallel_scan_one(txt, w0):
     from emme_b200 import parallel
     return parallel.solve_scan_texts([txt], [w0])
+
+
+@pytest.mark.parametrize("dim", [65, 100, 640, 1000, 2048])
+def test_lookahead_split_is_bitwise_neutral(dim, native_lib, monkeypatch):
+    """Single-level symmetric path with look-ahead (the rank-32 update split over two streams so that
+    the next panel starts early) against the same path without it: every entry sees the same
+    products in the same order, so delta must be identical to the last bit, graph replay included."""
+    A, B = _sym_case(dim, seed=21)
+    got = {}
+    for la in ("0", "1"):
+        monkeypatch.setenv("EMME_DENSE_LOOKAHEAD", la)
+        s = _trace_solver(dim)
+        got[la] = (s.trace_delta(A, B), s.trace_delta(A, B))
+        assert s.stats()["sym_steps"] == 2
+        s.close()
+    assert got["0"][0] == got["0"][1] == got["1"][0] == got["1"][1], got
+    ref = -1.0 / np.trace(np.linalg.solve(A, B))
+    assert abs(got["1"][0] - ref) <= 1e-12 * abs(ref)
