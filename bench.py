@@ -731,9 +731,26 @@ def bench_b200(args, rank, local_rank, world):
         pr, nr = inp_r.params()
         ss = parallel.ShardedEigenSolver(pr, nr, *inp_r.tables(), device=local_rank)
         tolr = inp_r.number("iteration_precision")
+        # parity first: seed + two iterates must reproduce a single-GPU solver bit for bit (the shards
+        # are disjoint and every element sees the same operations in the same order for any number of
+        # ranks); rank 0 runs the single-GPU solver, every rank compares with its result
         ss.seed(omega0 * 1.01)
+        sharded_its = []
         for _ in range(2):
             ss.newtonTraceSecantIteration()
+            sharded_its.append((ss.eigen_value, ss.d_eigen_value))
+        single_its = [None]
+        if rank == 0:
+            s1 = EigenSolver.from_input(inp_r, device=local_rank)
+            s1.seed(omega0 * 1.01)
+            its = []
+            for _ in range(2):
+                s1.newtonTraceSecantIteration()
+                its.append((s1.eigen_value, s1.d_eigen_value))
+            s1.close()
+            single_its = [its]
+        dist.broadcast_object_list(single_its, src=0)
+        bitwise = sum_over_ranks(1.0 if sharded_its == single_its[0] else 0.0) == world
         ss.seed(omega0)
         barrier()
         rsteps = min(args.steps, 20)
@@ -762,6 +779,7 @@ def bench_b200(args, rank, local_rank, world):
                        "host wall time of newtonTraceSecantIteration alone (dense step + assembly + secant)",
                "assemble_ms": max_over_ranks(asm / rsteps), "dense_ms": max_over_ranks(dns / rsteps),
                "pivot_fallbacks": ss.stats()["pivot_fallbacks"] - fb0,
+               "bitwise_equal_to_single_gpu": bool(bitwise),
                "dense_sharded": bool(ss.dense_sharded),
                "omega": [ss.eigen_value.real, ss.eigen_value.imag],
                "exchange": "assembly: peer stores from inside the kernel (CUDA IPC over NVLink), device-side "

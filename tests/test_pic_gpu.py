@@ -269,8 +269,13 @@ def test_sharded_markers_fused_exchange_one_device(world, case, native_lib, monk
     steps = int(g["steps"])
     markers = (g["eta"], g["v_para"], g["v_perp"], g["weight"])
     grp = parallel.LocalShardedPIC(p, markers, devices=[0] * world)
-    grp.step(dt, 2)
-    grp.step(dt, steps - 2)
+    try:
+        grp.step(dt, 2)
+        grp.step(dt, steps - 2)
+    except pic.capi.EmmeError as e:
+        if e.code == pic.capi.E_PEER:     # see tests/test_sharded_gpu.py::co_scheduled
+            pytest.skip(f"virtual ranks were not co-scheduled on this device: {e}")
+        raise
     hists = [s.field_history() for s in grp.ranks]
     for h in hists[1:]:
         assert np.array_equal(h, hists[0])
