@@ -46,11 +46,8 @@ struct emme_solver {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evd0 = nullptr, evd1 = nullptr;   // dense-step timing (created once, not per step)
-    emme::DenseAux aux{};             // side stream + events of the dense step's look-ahead
-    // EMME_DENSE_LOOKAHEAD=1: split the rank-32 update of the single-level path over two streams so
-    // that the next panel starts early.  Bitwise neutral (tests), measured neutral in time as well
-    // (dim 2048: 3.23 vs 3.23 ms, with and without stream priorities): off by default.
-    int use_lookahead = 0;
+    emme::DenseAux aux{};             // high-priority chain stream + fork/join events of the dense step
+    int use_lookahead = 1;            // EMME_DENSE_LOOKAHEAD=0: panel chain on the main stream (one stream)
     // emme_copy_matrix_async: device->host copies overlap the next iterate on their own stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_src = nullptr, ev_copy_done = nullptr;
@@ -224,12 +221,12 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     s->dim = std::fpclassify(p->beta_e) == FP_ZERO ? npoints : 2 * npoints;
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     {
-        // the handle's stream carries the dependent chain of the dense step (panels); the side stream
-        // of the look-ahead carries bulk updates that must yield SM slots to it
+        // the side stream carries the dependent chain of the dense step (panel factorisations): its
+        // short kernels take SM slots ahead of the bulk updates queued on the handle's stream
         int prio_low = 0, prio_high = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-        CU(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_high));
-        CU(cudaStreamCreateWithPriority(&s->aux.side, cudaStreamNonBlocking, prio_low));
+        CU(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_low));
+        CU(cudaStreamCreateWithPriority(&s->aux.side, cudaStreamNonBlocking, prio_high));
     }
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
@@ -466,14 +463,25 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
                 dp.serial = ++s->dense_serial;
                 dp.epoch = &s->peer_epoch;
                 CU(emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace, s->d_info,
-                                          s->d_flag, s->stream, &s->launches, &dp));
+                                          s->d_flag, s->stream, &s->launches, &dp,
+                                          s->use_lookahead ? &s->aux : nullptr));
             } else {
-                int rc = replay_graph(s, &s->sym_graph, &s->sym_graph_launches, [&](unsigned long long* nl) {
+                auto enqueue = [&](unsigned long long* nl) {
                     return emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace,
                                                   s->d_info, s->d_flag, s->stream, nl, nullptr,
                                                   s->use_lookahead ? &s->aux : nullptr);
-                });
-                if (rc) return rc;
+                };
+                // Large systems run the blocked path with the panel chain on a high-priority stream;
+                // replayed from a CUDA graph the chain's kernels lose most of that priority (dim 8192:
+                // 76.3 ms replayed, 73.9 ms launched directly, 78.7 ms on one stream) and the ~600
+                // launches of a step hide behind 70 ms of work anyway: launched directly from 4096 up.
+                const int nbo = emme::dense_sym_outer_block(s->dim);
+                if (s->use_lookahead && nbo >= 64 && nbo % 64 == 0 && s->dim >= 4096) {
+                    CU(enqueue(&s->launches));
+                } else {
+                    int rc = replay_graph(s, &s->sym_graph, &s->sym_graph_launches, enqueue);
+                    if (rc) return rc;
+                }
             }
         } else {
             if (!rhs_intact) {

@@ -527,10 +527,16 @@ struct GemmAcc {
     double re[2][4][2], im[2][4][2];
 };
 
-// acc = A[m0:m0+64, 0:K) * Bm[0:K, n0:n0+64) (rows beyond M / columns beyond N read as zero)
-__device__ __forceinline__ void zgemm_mainloop(GemmAcc& acc, const z_t* __restrict__ A, int lda,
-                                               const z_t* __restrict__ Bm, int ldb, int M, int N,
-                                               int K, int m0, int n0) {
+// acc = A[m0:m0+64, 0:K) * Bm[0:K, n0:n0+64) (rows beyond M / columns beyond N read as zero).
+// SUB: acc = Cin[tile] - A*B instead -- the accumulators START as the C tile (its loads are issued
+// right after the first operand stages, so their HBM latency hides behind the pipeline fill) and the
+// products are subtracted as they come; the caller's epilogue is then a plain store.  (The first
+// version formed A*B from zero and read-modified-wrote C afterwards: the exposed load latency of
+// that epilogue was 10-15 % of a K = 256 tile.)
+template <bool SUB>
+__device__ __forceinline__ void zgemm_mainloop_t(GemmAcc& acc, const z_t* __restrict__ A, int lda,
+                                                 const z_t* __restrict__ Bm, int ldb, int M, int N,
+                                                 int K, int m0, int n0, const z_t* __restrict__ Cin, int ldc) {
     extern __shared__ __align__(16) unsigned char g_smem_raw[];
     z_t* smem = reinterpret_cast<z_t*>(g_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -558,19 +564,26 @@ __device__ __forceinline__ void zgemm_mainloop(GemmAcc& acc, const z_t* __restri
             cp_async16(sB + k * G_LDB + bn, src, ok);
         }
     };
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc.re[i][j][0] = acc.re[i][j][1] = 0.0;
-            acc.im[i][j][0] = acc.im[i][j][1] = 0.0;
-        }
-
     const int nslab = (K + GK - 1) / GK;
 #pragma unroll
     for (int s0 = 0; s0 < GSTAGES - 1; ++s0) {
         if (s0 < nslab) issue(s0);
         cp_async_commit();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + wm * 16 + i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * q + e;
+                z_t c = make_double2(0., 0.);
+                if (SUB && m < M && n < N) c = Cin[(size_t)m * ldc + n];
+                acc.re[i][j][e] = c.x;
+                acc.im[i][j][e] = c.y;
+            }
+        }
     }
     for (int slab = 0; slab < nslab; ++slab) {
         cp_async_wait<GSTAGES - 2>();
@@ -588,19 +601,27 @@ __device__ __forceinline__ void zgemm_mainloop(GemmAcc& acc, const z_t* __restri
             for (int j = 0; j < 4; ++j) bf[j] = sB[(k4 + q) * G_LDB + wn * 32 + j * 8 + g];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const double nai = -af[i].y;
+                // SUB: acc -= a*b, i.e. the a fragment enters negated
+                const double ar = SUB ? -af[i].x : af[i].x, ai = SUB ? -af[i].y : af[i].y;
+                const double nai = -ai;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    dmma(acc.re[i][j], af[i].x, bf[j].x);
-                    dmma(acc.im[i][j], af[i].x, bf[j].y);
+                    dmma(acc.re[i][j], ar, bf[j].x);
+                    dmma(acc.im[i][j], ar, bf[j].y);
                     dmma(acc.re[i][j], nai, bf[j].y);
-                    dmma(acc.im[i][j], af[i].y, bf[j].x);
+                    dmma(acc.im[i][j], ai, bf[j].x);
                 }
             }
         }
     }
     cp_async_wait<0>();
     __syncthreads();   // the shared-memory ring may be reused by the caller / the next tile
+}
+
+__device__ __forceinline__ void zgemm_mainloop(GemmAcc& acc, const z_t* __restrict__ A, int lda,
+                                               const z_t* __restrict__ Bm, int ldb, int M, int N,
+                                               int K, int m0, int n0) {
+    zgemm_mainloop_t<false>(acc, A, lda, Bm, ldb, M, N, K, m0, n0, nullptr, 0);
 }
 
 // element (i, j, e) of a thread's accumulators is tile entry (acc_row(i), acc_col(j, e))
@@ -619,7 +640,7 @@ __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
                                                int K, int bx, int by) {
     const int m0 = by * GM, n0 = bx * GN;
     GemmAcc acc;
-    zgemm_mainloop(acc, A, lda, Bm, ldb, M, N, K, m0, n0);
+    zgemm_mainloop_t<true>(acc, A, lda, Bm, ldb, M, N, K, m0, n0, C, ldc);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int m = m0 + acc_row(i);
@@ -630,10 +651,7 @@ __device__ __forceinline__ void zgemm_sub_tile(z_t* __restrict__ C, int ldc,
             for (int e = 0; e < 2; ++e) {
                 const int n = n0 + acc_col(j, e);
                 if (n >= N) continue;
-                z_t c = C[(size_t)m * ldc + n];
-                c.x -= acc.re[i][j][e];
-                c.y -= acc.im[i][j][e];
-                C[(size_t)m * ldc + n] = c;
+                C[(size_t)m * ldc + n] = make_double2(acc.re[i][j][e], acc.im[i][j][e]);
             }
         }
     }
@@ -1685,38 +1703,6 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
     if (NBO % GN != 0 || NBO == NB) {
         // ---- single level / unaligned outer block: one GPU only (small systems, launch bound) ----
         if (P > 1) return cudaErrorInvalidValue;
-        if (NBO == NB && aux && aux->side && dim > 2 * NB) {
-            // Single level with LOOK-AHEAD (small systems are bound by the panel chain: 2 dim/32
-            // dependent launches).  The rank-32 update of panel k is split into (a) what panel k+1
-            // reads -- its 32 columns of W and its 32 rows of Y -- on the main stream, followed at once
-            // by panel k+1, and (b) the rest, on a side stream, concurrent with (a) and panel k+1;
-            // (a) of the next step waits for (b).  Every entry sees the same products in the same
-            // order as without the split.  Captured into the step's CUDA graph as fork/join edges.
-            bool side_busy = false;
-            for (int k0 = 0; k0 < dim; k0 += NB) {
-                const int jb = dim - k0 < NB ? dim - k0 : NB;
-                const int ke = k0 + jb;
-                const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke + tile - 1) / tile;
-                panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, 0, ke, n_row,
-                                                                                tile, g_tau, d_flag, dvec);
-                ++nl;
-                if (ke >= dim) break;
-                const int nn = dim - ke < NB ? dim - ke : NB;       // width of the next panel
-                // (b): W[ke+nn:, ke+nn:) lower block triangle and Y[ke+nn:, 0:ke)
-                DCHK(cudaEventRecord(aux->ev_panel, stream));
-                DCHK(cudaStreamWaitEvent(aux->side, aux->ev_panel, 0));
-                const bool has_b = update_on(aux->side, ke + nn, dim - ke - nn, ke + nn, dim - ke - nn, dim - ke - nn,
-                                             0, ke, k0, jb);
-                // (a): W[ke:, ke:ke+nn) and Y[ke:ke+nn, 0:ke) -- after (b) of the previous panel
-                if (side_busy) DCHK(cudaStreamWaitEvent(stream, aux->ev_rest, 0));
-                update_on(stream, ke, dim - ke, ke, nn, nn, 0, ke, k0, jb);
-                if (has_b) {
-                    DCHK(cudaEventRecord(aux->ev_rest, aux->side));
-                    side_busy = true;
-                }
-            }
-            if (side_busy) DCHK(cudaStreamWaitEvent(stream, aux->ev_rest, 0));   // join
-        } else
         for (int K0 = 0; K0 < dim; K0 += NBO) {
             const int JB = dim - K0 < NBO ? dim - K0 : NBO;
             const int KE = K0 + JB;
@@ -1748,7 +1734,16 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
             int c = from + ((me - from) % P + P) % P;
             return c;
         };
-        auto factor_publish = [&](int K) -> cudaError_t {
+        // The dependent chain of the step -- bring block K+1 up to date, factor it, publish it -- runs
+        // on its own HIGH-priority stream, concurrently with the bulk update of step K on the main
+        // stream: the panel kernels are latency bound (a 32 x 32 block factorisation per launch) and
+        // need few SMs, so on one GPU the chain (13 % of the step at dim 8192) disappears behind the
+        // bulk, and on several GPUs the owner of a panel is not held up by its own factorisation.
+        // Fork: the chain waits for `ev_ready` (panel K available and every earlier update done);
+        // join: the next step's first use of panel K+1 waits for `ev_chain`.
+        cudaStream_t chain = (aux && aux->side) ? aux->side : stream;
+        const bool two_streams = chain != stream;
+        auto factor_publish = [&](int K, cudaStream_t st) -> cudaError_t {
             const int K0 = K * NBO;
             const int JB = dim - K0 < NBO ? dim - K0 : NBO;
             const int KE = K0 + JB;
@@ -1756,10 +1751,10 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                 const int jb = KE - k0 < NB ? KE - k0 : NB;
                 const int ke = k0 + jb;
                 const int n_row = (dim - ke + tile - 1) / tile, n_col = (ke - K0 + tile - 1) / tile;
-                panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, stream>>>(W, Y, ld, dim, k0, jb, K0, ke, n_row,
-                                                                                tile, g_tau, d_flag, dvec);
+                panel_sym_kernel<<<n_row + n_col, 128, PS_SMEM_BYTES, st>>>(W, Y, ld, dim, k0, jb, K0, ke, n_row,
+                                                                            tile, g_tau, d_flag, dvec);
                 ++nl;
-                if (ke < KE) update(ke, dim - ke, ke, KE - ke, KE - ke, K0, ke - K0, k0, jb);
+                if (ke < KE) update_on(st, ke, dim - ke, ke, KE - ke, KE - ke, K0, ke - K0, k0, jb);
             }
             if (P > 1) {
                 // the owner of the NEXT panel is on the critical path (it must update its block with
@@ -1771,19 +1766,19 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                 const int next = (K + 1 < nb) ? owner(K + 1) : -1;
                 unsigned first = (next >= 0 && next != me) ? (1u << next) : 0u;
                 if (first) {
-                    publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB, first);
-                    DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, stream, first));
+                    publish_panel_kernel<<<blocks, 256, 0, st>>>(sp, ld, dim, K0, JB, first);
+                    DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, st, first));
                     nl += 2;
                 }
                 if (all & ~first) {
-                    publish_panel_kernel<<<blocks, 256, 0, stream>>>(sp, ld, dim, K0, JB, all & ~first);
-                    DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, stream, all & ~first));
+                    publish_panel_kernel<<<blocks, 256, 0, st>>>(sp, ld, dim, K0, JB, all & ~first);
+                    DCHK(launch_peer_signal(peers->flags, PEER_W_PANEL + K, peers->serial, st, all & ~first));
                     nl += 2;
                 }
             }
             return cudaGetLastError();
         };
-        auto shard_update = [&](int K0, int JB, int wblk0, int wblk_end, int yblk0, int yblk_end) {
+        auto shard_update = [&](cudaStream_t st, int K0, int JB, int wblk0, int wblk_end, int yblk0, int yblk_end) {
             // W blocks wblk0, wblk0+P, ... < wblk_end; Y blocks yblk0, yblk0+P, ... < yblk_end
             const int KE = K0 + JB;
             const int M = dim - KE;
@@ -1793,11 +1788,12 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
             const int nyb = yblk0 < yblk_end ? (yblk_end - yblk0 + P - 1) / P : 0;
             if (nwb + nyb == 0) return;
             dim3 g((nwb + nyb) * tpb, (M + GM - 1) / GM);
-            shard_update_kernel<<<g, 256, G_SMEM_BYTES, stream>>>(W, Y, S, ld, dim, K0, JB, wblk0, nwb * tpb, yblk0,
-                                                                  P, NBO);
+            shard_update_kernel<<<g, 256, G_SMEM_BYTES, st>>>(W, Y, S, ld, dim, K0, JB, wblk0, nwb * tpb, yblk0,
+                                                              P, NBO);
             ++nl;
         };
-        if (owner(0) == me) DCHK(factor_publish(0));
+        if (owner(0) == me) DCHK(factor_publish(0, stream));
+        bool chain_pending = false;
         for (int K = 0; K < nb; ++K) {
             const int K0 = K * NBO;
             const int JB = dim - K0 < NBO ? dim - K0 : NBO;
@@ -1810,13 +1806,24 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                         W, dvec, ld, dim, K0, JB);
                     ++nl;
                 }
+            } else if (chain_pending) {
+                DCHK(cudaStreamWaitEvent(stream, aux->ev_rest, 0));      // join: my chain factored panel K
+                chain_pending = false;
             }
-            // look-ahead first (the critical path of the whole step runs through the panels): the
-            // owner of panel K+1 brings that block up to date, factors and publishes it
+            // look-ahead (the critical path of the whole step runs through the panels): the owner of
+            // panel K+1 brings that block up to date, factors and publishes it -- on the chain stream
             const bool ahead = KE < dim && K + 1 < nb && owner(K + 1) == me;
             if (ahead) {
-                shard_update(K0, JB, K + 1, K + 2, 0, 0);
-                DCHK(factor_publish(K + 1));
+                if (two_streams) {
+                    DCHK(cudaEventRecord(aux->ev_panel, stream));        // fork: panel K + all earlier updates
+                    DCHK(cudaStreamWaitEvent(chain, aux->ev_panel, 0));
+                }
+                shard_update(chain, K0, JB, K + 1, K + 2, 0, 0);
+                DCHK(factor_publish(K + 1, chain));
+                if (two_streams) {
+                    DCHK(cudaEventRecord(aux->ev_rest, chain));
+                    chain_pending = true;
+                }
             }
             // rows K of my columns of Y become final: Y_K <- M_KK Y_K (blocks < K), via the scratch S
             const int y0 = first_own(0);
@@ -1834,9 +1841,10 @@ cudaError_t launch_trace_sym(void* Wv, void* Yv, void* YTv, const void* Bv, int 
                                        cudaMemcpyDeviceToDevice, stream));
             }
             if (KE >= dim) continue;
-            if (ahead) shard_update(K0, JB, K + 1 + P, nb, y0, K + 1);
-            else shard_update(K0, JB, first_own(K + 1), nb, y0, K + 1);
+            if (ahead) shard_update(stream, K0, JB, K + 1 + P, nb, y0, K + 1);
+            else shard_update(stream, K0, JB, first_own(K + 1), nb, y0, K + 1);
         }
+        if (chain_pending) DCHK(cudaStreamWaitEvent(stream, aux->ev_rest, 0));
         if (P > 1) {
             // every rank's final rows of Y have arrived everywhere
             DCHK(launch_peer_barrier(peers->flags, ++*peers->epoch, stream));

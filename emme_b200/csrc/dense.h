@@ -44,7 +44,8 @@ struct DensePeers {
     unsigned long long serial;
     unsigned long long* epoch;
 };
-// a side stream and two events (owned by the handle) for the look-ahead of the single-level path
+// a high-priority side stream and two events (owned by the handle): the panel chain of the blocked
+// symmetric path runs there, concurrently with the bulk update on the main stream
 struct DenseAux {
     cudaStream_t side;
     cudaEvent_t ev_panel, ev_rest;
