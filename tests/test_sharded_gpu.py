@@ -146,11 +146,12 @@ def test_sharded_dense_step_bitwise(dim, world, nbo, native_lib, monkeypatch):
         assert all(r.stats()["sym_steps"] == rep + 1 for r in g.ranks)
     # a matrix that needs interchanges: every rank sees the OR of the flags and takes the same fallback
     A2 = A.copy()
-    A2[7, 7] = 1e-9
+    A2[0, 0] = 1e-9
     g._all(lambda s: out.__setitem__(g.ranks.index(s), s.trace_delta(A2, B)))
     ref2 = -1.0 / np.trace(np.linalg.solve(A2, B))
     assert all(abs(d - ref2) <= 1e-10 * abs(ref2) for d in out), (out, ref2)
-    assert all(r.stats()["pivot_fallbacks"] == 1 for r in g.ranks)
+    fb = [(r.stats()["pivot_fallbacks"], r.stats()["sym_steps"]) for r in g.ranks]
+    assert all(f == (1, 2) for f in fb), fb
     g.close()
     one.close()
     monkeypatch.setenv("EMME_DENSE_NBO", "0")
