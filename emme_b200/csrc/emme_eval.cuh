@@ -363,10 +363,12 @@ EMME_HD NodeConst node_const(const RunConst& rc, double x) {
 // minimax kernels for sin/cos on [-pi/4, pi/4] (error < 2^-58) and a degree-13 Taylor kernel for
 // exp on [-ln2/2, ln2/2] (truncation 4e-18).  |b| >= 2^19 (never seen in practice) and a outside
 // [-700, 700] fall back to the library.  tests/test_emul.py::test_lean_cexp pins the product to <= 3 ulp per component.
-// Measured on B200 (N = 8192): 122.2 ms with it, 121.0 ms with the library calls -- the kernel is
-// not issue bound, so it is OFF by default and kept as a tested alternative.
+// Measured on B200 (N = 8192).  Round 1, before the kernel became issue-slot bound: 122.2 ms with
+// it against 121.0 ms with the library calls (kept OFF).  Round 2, on the shipped kernel: 100.95 ms
+// with it against 102.21 ms (C1, C3 at N = 1024 unchanged) -- ON by default; -DEMME_LEAN_CEXP=0
+// restores the library calls.
 #ifndef EMME_LEAN_CEXP
-#define EMME_LEAN_CEXP 0
+#define EMME_LEAN_CEXP 1
 #endif
 
 // coefficients of cexp_lean: in __constant__ memory on the device so that they are direct
