@@ -205,10 +205,13 @@ EMME_HD void bessel_i_alter(cplx z, cplx zc, cplx& y0, cplx& y1, cplx& mu, EvalC
     int n = n0;
     double dn = (double)n0;
     // Forward recurrence p_{k+1} = p_{k-1} - (2n/z) p_k until |p|^2 exceeds the threshold.  Only the
-    // STOPPING INDEX N is used below (the backward pass restarts from y_N = 1), and the result does
-    // not depend on it beyond 1/|p_N|^2 ~ 2.5e-15: the search therefore runs in FP32 on the
-    // otherwise idle FP32 pipe (relative error ~1e-6 in |p|^2 can move N by one only when |p_N|^2
-    // sits within 1e-6 of the threshold).
+    // STOPPING INDEX N is used below (the backward pass restarts from y_N = 1; the VALUE p_N only
+    // scales the returned triple): the search therefore runs in FP32 on the otherwise idle FP32
+    // pipe (relative error ~1e-6 in |p|^2 can move N by one only when |p_N|^2 sits within 1e-6 of
+    // the threshold).  N itself must be the reference's: stopping at |p| > 2e7 leaves the
+    // reference's ratios with a truncation error of ~1e-9, so a different start index -- even a
+    // larger, more accurate one -- moves them by 1e-9..1e-11, beyond the 1e-10 parity bar (tried in
+    // round 2 with a tabulated upper bound).
     if (n2 >= 1e-10) {
         const float thr2 = (float)(THRESHOLD * THRESHOLD);
         const float zr = (float)zc.re, zi = (float)zc.im;
