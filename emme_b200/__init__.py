@@ -5,14 +5,6 @@ Python here is a thin host-side mirror of the reference's solver entry points
 (EigenSolver, solve_once_eigen, the scan generator) over that C ABI; the compute path is the
 CUDA library and fails loudly without it.
 """
-import os as _os
-
-# Kernels are loaded when the library is, not lazily on first launch: a lazy load can wait for the
-# context to drain, which a device-side wait of the multi-GPU protocol (csrc/peer.cu) may be holding
-# up.  Only effective if set before the process initialises CUDA; the library also preloads its own
-# kernels when a peer group is formed.
-_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 from .capi import EmmeError, EmmeParams, EmmePicParams, EmmeStats, load  # noqa: F401
 from .solver import EigenSolver, Input, scan_values, solve_once_eigen  # noqa: F401
 from .pic import PIC_State, Integrator, calculate_omega, solve_once_pic  # noqa: F401

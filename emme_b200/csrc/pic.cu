@@ -600,6 +600,8 @@ __global__ void pic_sort_scatter_kernel(long n, double scale, int identity, cons
     }
 }
 
+cudaError_t pic_preload();
+
 // un-normalised p_weight of one marker (include/solver_pic.h:229-232)
 inline double pweight_raw(const emme_pic_params* p, double vp, double vq, double wa, double wb) {
     return vq * std::exp(-(vp * vp * wa + vq * vq * wb) / (2 * p->vt * p->vt));
@@ -789,6 +791,7 @@ int create_impl(const emme_pic_params* p, long n_total, long first, long n, cons
         s->xch_flag_offset = (s->xch_flag_offset + 255) / 256 * 256;
         size_t bytes = s->xch_flag_offset + sizeof(unsigned long long) * ((size_t)shard_count * nblk + 1);
         if (bytes < (2u << 20)) bytes = 2u << 20;
+        CU(pic_preload());
         CU(cudaMalloc(&s->xch, bytes));
         CU(cudaMemsetAsync(s->xch, 0, bytes, s->stream));
         d.peers.n = shard_count;
@@ -816,6 +819,21 @@ int ensure_perm(emme_pic* s) {
     CU(cudaMemcpyAsync(s->perm.data(), s->d_perm, sizeof(long) * s->n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return 0;
+}
+
+// load every kernel a sharded step can launch before the first device-side wait exists (CUDA loads
+// kernels lazily, and a load may have to wait for the context to drain; see dense_preload)
+cudaError_t pic_preload() {
+    cudaFuncAttributes a;
+    const void* ks[] = {(const void*)pic_stage_kernel<true, true>, (const void*)pic_stage_kernel<false, true>,
+                        (const void*)pic_stage_kernel<true, false>, (const void*)pic_stage_kernel<false, false>,
+                        (const void*)pic_field_kernel, (const void*)pic_init_kernel<true>,
+                        (const void*)pic_init_kernel<false>};
+    for (const void* k : ks) {
+        cudaError_t e = cudaFuncGetAttributes(&a, k);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 void set_peer(emme_pic* s, int r, void* base) {
