@@ -22,8 +22,10 @@ arms, so the seeding overhead is charged against the B200 arm alone).
     N > 1   scan-parallel (weak scaling): every rank iterates its own scan point (k_rho), no
             collective on the data path
 
-The headline line is printed as soon as it is known ("provisional": true); the extras follow,
-each fenced (a failing extra records {"error": ...}), and the complete line is printed last.
+Exactly ONE JSON line is printed.  The headline is complete before any extra leg starts; every extra
+is fenced (a failing extra records {"error": ...}), and if the run ends before the last leg has
+finished (a hang -> watchdog, an uncaught exception, SIGTERM) the line is printed anyway with the
+headline and the legs that did finish ("incomplete": ...).
 Extras: c1 / c3 (converged-eigenvalue time of input-example.json and of the stellarator case, with
 the reference's full solve timed in the same run), c5 (64-wavenumber scan over the ranks), sweep
 (512 .. 8192, row-sharded over the ranks when N > 1), row_sharded (one N=8192 problem over N GPUs:
@@ -335,7 +337,7 @@ def bench_pic(device, hbm_peak):
     return out
 
 
-def bench_converged(name, path, golden_key, device, with_reference):
+def bench_converged(name, path, golden_key, device, with_reference, peak_tf=None):
     """north_star target 1: converged-eigenvalue time of an input file through solve_once_eigen
     with HOST buffers (parse + tables + create + seed + iterates + eigen_matrix download), next to
     the reference's own full solve (ref_driver newton = its ctor + iteration loop) timed in the
@@ -350,7 +352,6 @@ def bench_converged(name, path, golden_key, device, with_reference):
     t0 = time.perf_counter()
     w, its, _ = solve_once_eigen(inp, inp.initial_guess(), solver=s)
     t1 = time.perf_counter()
-    asm_ms = dense_ms = 0.0
     st = s.stats()
     s.close()
     # cold: everything a caller of the reference's solve_once_eigen pays, host buffers both ways
@@ -362,13 +363,21 @@ def bench_converged(name, path, golden_key, device, with_reference):
     s2._lib.emme_copy_matrix(s2._h, 0, A.ctypes.data)
     s2.close()
     t3 = time.perf_counter()
-    out = {"workload": name, "npoints": inp.params()[1], "dim": st and s2.dim,
+    out = {"workload": name, "npoints": inp.params()[1], "dim": s2.dim,
            "converged_eigenvalue_s": t1 - t0, "newton_iterates": len(its),
            "e2e_cold_s": t3 - t2,
            "e2e_cold_includes": "input.json parse, tables, emme_create (device buffers), seed, iterates, "
                                 "eigen_matrix download to host memory, emme_destroy",
            "omega": [w.real, w.imag], "last_assemble_ms": st["assemble_ms"], "last_dense_ms": st["dense_ms"]}
-    del asm_ms, dense_ms
+    fl = algorithmic_flops(st)
+    out["roofline"] = {"kernel": "assemble_kernel (kernel 1), last assembly of the solve", "bound": "fp64",
+                       "achieved": fl / (st["assemble_ms"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                       "frac": (fl / (st["assemble_ms"] * 1e-3) / 1e12 / peak_tf) if peak_tf else None,
+                       "evals": st["evals"], "integrals": st["integrals"]}
+    d3 = float(s2.dim) ** 3
+    out["roofline_dense"] = {"kernel": "kernel 2 (symmetric path, 4 dim^3 flops)", "bound": "fp64",
+                             "achieved": st["dense_flops"] / (st["dense_ms"] * 1e-3) / 1e12 if st["dense_ms"] else None,
+                             "peak": peak_tf, "unit": "TFLOP/s", "flops": st["dense_flops"], "dim3": d3}
     try:
         gold = json.loads((GOLDEN / "golden.json").read_text())["newton"][golden_key]["final"]
         out["golden_omega"] = gold[:2]
@@ -411,19 +420,30 @@ def bench_b200(args, rank, local_rank, world):
     dim = n
     solver = EigenSolver.from_input(inp, device=local_rank)
     ext = torch.cuda.ExternalStream(solver.stream(), device=local_rank)
-    state = {"line": None, "extras": {}, "printed_final": False}
+    state = {"line": None, "extras": {}, "printed_final": False, "emitted": False}
+    import atexit
+    import signal
+    atexit.register(lambda: emit(False))            # an exception or sys.exit after the headline is known
+
+    def on_term(signum, _frame):
+        emit(False)
+        os._exit(0 if state["emitted"] or rank != 0 else 1)
+    signal.signal(signal.SIGTERM, on_term)
 
     def emit(final):
-        if rank != 0 or state["line"] is None:
+        """ONE JSON line on stdout, always: the complete line at the end of a normal run; if the run
+        ends any other way (an extra leg that hangs -> watchdog, an uncaught exception, SIGTERM) the
+        headline that was already known, with whatever extras had finished."""
+        if rank != 0 or state["line"] is None or state["emitted"]:
             return
+        state["emitted"] = True
         line = dict(state["line"])
-        if final:
-            line.update(state["extras"])
-            line["bench_wall_s"] = time.time() - T_START
-        else:
-            line["provisional"] = True
-            line["note"] = "headline only; the complete line (same keys + extras) is printed last"
-        print(json.dumps(line), flush=True)
+        line.update(state["extras"])
+        line["bench_wall_s"] = time.time() - T_START
+        if not final:
+            line["incomplete"] = "the run ended before every extra leg had finished; headline and finished legs only"
+        sys.stdout.write(json.dumps(line) + "\n")
+        sys.stdout.flush()
 
     def watchdog():
         # never lose the line: if an extra hangs (a peer that died inside a collective), print what
@@ -431,8 +451,7 @@ def bench_b200(args, rank, local_rank, world):
         if not state["printed_final"]:
             state["extras"]["watchdog"] = f"an extra leg did not finish within {DEADLINE_S:.0f} s; line printed by the watchdog"
             state["printed_final"] = True
-            emit(True)
-            sys.stdout.flush()
+            emit(False)
             os._exit(0)
 
     wd = threading.Timer(max(30.0, DEADLINE_S - (time.time() - T_START)), watchdog)
@@ -622,7 +641,10 @@ def bench_b200(args, rank, local_rank, world):
         state["line"] = line
     solver.close()
     del pin_A
-    emit(False)
+    if rank == 0:       # the headline is known: a copy for whoever watches the run (stderr, not the result line)
+        sys.stderr.write("[bench] headline: " + json.dumps({k: state["line"][k] for k in
+                         ("metric", "value", "unit", "n_gpus", "ms_per_step", "e2e")}) + "\n")
+        sys.stderr.flush()
 
     # ------------------------------------------------------------------ extras, each fenced
     extras = state["extras"]
@@ -665,7 +687,7 @@ def bench_b200(args, rank, local_rank, world):
                "matrix_elements_per_s": 1024 * 1024 * (iters + 2 * len(recs)) / secs,
                "converged": sum(1 for r in recs if r.get("converged")),
                "failed": sum(1 for r in recs if r.get("eigenvalue") == "NaN"),
-               "scaling": "weak-ish: fixed 64 points over N GPUs", "n_gpus": world,
+               "scaling": "strong: the same 64 points over N GPUs", "n_gpus": world,
                "eigenvalues": [r.get("eigenvalue") for r in recs]}
         try:
             gold = json.loads((GOLDEN / "c5.json").read_text())["points"]
@@ -818,10 +840,11 @@ def bench_b200(args, rank, local_rank, world):
     if not args.quick:
         if rank == 0 and world == 1:
             fenced("c1", lambda: bench_converged("input-example.json (method=eigen, omega_d_coeff=1.0), N=1024",
-                                                 workloads.C1_PATH, "c1", local_rank, not args.no_reference))
+                                                 workloads.C1_PATH, "c1", local_rank, not args.no_reference,
+                                                 peak_tf.value))
             fenced("c3", lambda: bench_converged("input-stellarator-example.json + the 7 missing keys (SURVEY 8d): "
                                                  "EM, GK31, N=1024, dim=2048", workloads.C3_PATH, "c3", local_rank,
-                                                 not args.no_reference and time_left() > 300))
+                                                 not args.no_reference and time_left() > 300, peak_tf.value))
         fenced("c5", leg_c5)
         fenced("sweep", leg_sweep)
         if world > 1:
