@@ -462,9 +462,11 @@ static int dense_delta(emme_solver* s, zc* delta, RestoreRhs restore_rhs) {
                 }
                 dp.serial = ++s->dense_serial;
                 dp.epoch = &s->peer_epoch;
+                // one stream: with several ranks the step is bound by the panel chain itself, and chain
+                // kernels that wait for bulk CTAs to retire make it longer (N = 8192, chain stream on /
+                // off: 43.6 / 43.3 ms on 2 GPUs, 28.4 / 25.1 on 4, 20.8 / 17.9 on 8; one GPU 73.9 / 78.7)
                 CU(emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace, s->d_info,
-                                          s->d_flag, s->stream, &s->launches, &dp,
-                                          s->use_lookahead ? &s->aux : nullptr));
+                                          s->d_flag, s->stream, &s->launches, &dp, nullptr));
             } else {
                 auto enqueue = [&](unsigned long long* nl) {
                     return emme::launch_trace_sym(s->W, s->Y, s->YT, s->Ad, s->dim, s->d_sym_ws, s->d_trace,
