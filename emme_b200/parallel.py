@@ -149,7 +149,9 @@ def solve_scan_texts(texts, starts, device=0, group=None):
                        converged=bool(abs(iters[-1][1]) < abs(inp.number("iteration_precision") * w)))
         except Exception as e:                       # noqa: BLE001 - recorded, scan continues
             rec.update(eigenvalue="NaN", reason=str(e))
-            if solver is not None:                   # a failed point must not poison the next one
+            # a numerical failure ("Linear solve failed", a singular pivot) leaves the handle healthy
+            # (tests/test_newton_gpu.py); only a device or peer error retires it
+            if solver is not None and getattr(e, "code", None) in (capi.E_CUDA, capi.E_PEER, capi.E_NO_DEVICE):
                 solver.close()
                 solver = None
         local.append((k, rec))
