@@ -1020,10 +1020,14 @@ int emme_pic_step(emme_pic* s, double dt, int nsteps) {
         }
         s->launches = before;
         cudaError_t e2 = cudaStreamEndCapture(s->stream, &g);
-        if (e != cudaSuccess) return capi_fail(EMME_E_CUDA, std::string("stage launch: ") + cudaGetErrorString(e));
-        CU(e2);
-        CU(cudaGraphInstantiate(&s->graph, g, 0));
-        CU(cudaGraphDestroy(g));
+        if (e == cudaSuccess) e = e2;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&s->graph, g, 0);
+        if (g) cudaGraphDestroy(g);          // on every path: a failed capture must not leak the graph
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s->graph = nullptr;
+            return capi_fail(EMME_E_CUDA, std::string("step graph: ") + cudaGetErrorString(e));
+        }
         s->graph_dt = dt;
     }
     CU(cudaEventRecord(s->ev0, s->stream));
