@@ -257,7 +257,7 @@ __device__ __forceinline__ void panel_body(Comm& comm, z_t* __restrict__ W, int 
 // never interchanges rows.  This kernel factors a panel WITHOUT interchanges -- which removes the
 // per-column pivot search and with it every inter-CTA dependency -- and records, for every
 // multiplier it forms, whether partial pivoting would have accepted the diagonal
-// (|a_ic| <= tau*|a_cc| with tau = 1 by default).  If the flag stays clear the factorisation IS
+// (|a_ic| <= tau*|a_cc|, tau = 32: threshold pivoting, see g_tau).  If the flag stays clear the factorisation IS
 // the partial-pivoting one; if it is raised the host discards the result and repeats the dense
 // step with the pivoting kernels above.  Every CTA first factors the jb x jb diagonal block
 // redundantly in shared memory (one warp), then each thread eliminates its own row against it.
