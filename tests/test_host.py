@@ -165,3 +165,27 @@ def test_host_program_pic_fails_loudly_without_gpu(tmp_path, native_lib):
         pytest.skip("a CUDA device is present")
     r = _run_emme(tmp_path, cases.input_path("pic_n32").read_text())
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_workload_texts_parse_and_match_goldens(native_lib):
+    """emme_b200/workloads.py: the input texts of the BASELINE configs parse with the host layer, the C4
+    sweep keeps C1's physics, and the C5 points are the ones the goldens were generated from."""
+    import json
+    from emme_b200 import Input, workloads
+    c1 = Input(workloads.C1_PATH)
+    p1, n1 = c1.params()
+    for n in workloads.C4_SIZES:
+        inp = Input(text=workloads.c4_text(n))
+        p, nn = inp.params()
+        assert nn == n and p.q == p1.q and p.tau == p1.tau and p.omega_s_i == p1.omega_s_i
+        assert abs(p.dx * (n - 1) - p1.dx * (n1 - 1)) <= 1e-12          # same domain, Grid::dx = 2L/(n-1)
+    pts = workloads.c5_points()
+    assert len(pts) == 64 and pts[0][0] == 0.05 and pts[63][0] == 0.68
+    assert len({round(k, 2) for k, _, _ in pts}) == 64
+    gold = json.loads((cases.GOLD / "c5.json").read_text())["points"]
+    for k, g in gold.items():
+        k_rho, w0, txt = workloads.c5_point(int(k))
+        assert k_rho == g["k_rho"] and [w0.real, w0.imag] == g["omega0"]
+        inp = Input(text=txt)
+        assert inp.number("k_rho") == k_rho and inp.initial_guess() == w0
+    assert workloads.workload_name(8192).startswith("C4 sweep point")

@@ -115,3 +115,77 @@ def test_marker_shard_partition_is_exact():
 
 def test_gather_without_process_group_is_identity():
     assert parallel.gather_results([(1, "b"), (0, "a")]) == ["a", "b"]
+
+
+def _pw_worker(rank, world, port, out):
+    """from_seed's host logic over gloo: every rank draws ITS block from its own mt19937 stream, the
+    un-normalised p_weight sums are added with one all-reduce, and the blocks tile the marker range."""
+    sys.path.insert(0, str(cases.ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from emme_b200 import Input, pic
+        p, _, _, _ = pic.pic_params(Input(cases.input_path("pic_n64_wb")))     # water-bag weights != 1
+        n_total = 10007
+        first, count = parallel.marker_shard(n_total, rank, world)
+        block = pic.load_markers(p, count, seed=3 + rank)
+        part = pic.pweight_sum(p, block[1], block[2])
+        t = torch.tensor([part, float(count), float(first)], dtype=torch.float64)
+        parts = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, t)
+        tot = torch.tensor([part], dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            torch.save({"parts": [x.tolist() for x in parts], "total": float(tot), "n_total": n_total}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_block_markers_and_pweight_sum(tmp_path, native_lib):
+    out = tmp_path / "pw.pt"
+    mp.spawn(_pw_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    parts = res["parts"]
+    assert sum(int(x[1]) for x in parts) == res["n_total"]
+    assert int(parts[0][2]) == 0 and int(parts[1][2]) == int(parts[0][1])      # contiguous blocks
+    assert abs(sum(x[0] for x in parts) - res["total"]) <= 1e-12 * res["total"]
+    assert all(x[0] > 0 for x in parts)
+
+
+def test_pweight_sum_is_additive_over_blocks(native_lib):
+    """emme_pic_pweight_sum over the blocks of a marker set adds up to the sum over the whole set (to
+    rounding: the reference sums sequentially), for unit and non-unit water-bag weights."""
+    from emme_b200 import Input, pic
+    for case in ("pic_n32", "pic_n64_wb"):
+        p, _, _, _ = pic.pic_params(Input(cases.input_path(case)))
+        m = pic.load_markers(p, 5000, seed=9)
+        whole = pic.pweight_sum(p, m[1], m[2])
+        parts = 0.0
+        for r in range(3):
+            first, count = parallel.marker_shard(5000, r, 3)
+            parts += pic.pweight_sum(p, m[1][first:first + count], m[2][first:first + count])
+        assert abs(parts - whole) <= 1e-13 * whole
+        if case == "pic_n32":                    # unit weights: p_weight is v_perp itself
+            assert whole == float(np.add.reduce(m[2], dtype=np.float64)) or abs(whole - m[2].sum()) <= 1e-12 * whole
+
+
+def test_column_block_ownership_covers_every_block():
+    """The column-block-cyclic ownership of the sharded dense step (csrc/dense.cu: block K belongs to
+    rank K mod P; first_own(from) = smallest own block >= from) restated: every block has exactly one
+    owner and the look-ahead split (block K+1 alone, then K+1+P, ...) visits each own block once."""
+    def first_own(frm, me, P):
+        return frm + ((me - frm) % P + P) % P
+    for P in (1, 2, 3, 4, 8):
+        for nb in (1, 2, 5, 9, 32, 33):
+            for K in range(nb):
+                seen = []
+                for me in range(P):
+                    ahead = K + 1 < nb and (K + 1) % P == me
+                    blocks = list(range(first_own(K + 1, me, P), nb, P))
+                    if ahead:
+                        assert blocks[0] == K + 1
+                        assert list(range(K + 1 + P, nb, P)) == blocks[1:]
+                    assert all(b % P == me and b > K for b in blocks)
+                    seen += blocks
+                assert sorted(seen) == list(range(K + 1, nb))
