@@ -13,8 +13,9 @@ int main(int argc, char** argv) {
             const int a = i < j ? i : j, b = i < j ? j : i;
             h[(size_t)i * dim + j] = i == j ? make_double2(2.0, 0.1) : make_double2(0.3 * sin(0.37 * a + 0.11 * b) / sqrt((double)dim), 0.2 * cos(0.23 * a - 0.07 * b) / sqrt((double)dim));
         }
-    double2 *W, *Y;
+    double2 *W, *Y, *dvec;
     int *flag, *info;
+    cudaMalloc(&dvec, sizeof(double2) * dim);
     cudaMalloc(&W, sizeof(double2) * dim * dim);
     cudaMalloc(&Y, sizeof(double2) * dim * dim);
     cudaMalloc(&flag, 4);
