@@ -349,8 +349,13 @@ panel_cluster_kernel(z_t* __restrict__ W, int ld, int dim, int k0, int jb, int* 
 
 // largest cluster size (power of two <= CLUSTER_MAX) the device can co-schedule for this kernel
 static int panel_cluster_limit() {
-    static int limit = -1;
-    if (limit >= 0) return limit;
+    static int limit_on[64];
+    static bool known[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& limit = limit_on[dev & 63];
+    if (known[dev & 63]) return limit;      // per device: the non-portable cluster attribute is, too
+    known[dev & 63] = true;
     limit = 0;
     if (cudaFuncSetAttribute(panel_cluster_kernel<CL_TPB>,
                              cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -1123,8 +1128,14 @@ __global__ void ydiag_kernel(const ShardPtrs sp, z_t* __restrict__ S, int ld, in
 __global__ void shard_update_kernel(z_t* __restrict__ W, z_t* __restrict__ Y, const z_t* __restrict__ S, int ld, int dim,
                                     int K0, int JB, int wblk0, int nwt, int yblk0, int P, int nbo);
 
+// function attributes are per DEVICE: a process that drives several GPUs (LocalShardedGroup, the
+// launcher-free binding of INTEGRATION.md) must set them on each
 static cudaError_t gemm_setup() {
-    static bool done = false;
+    static bool done_on[64] = {};
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    bool& done = done_on[dev & 63];
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G_SMEM_BYTES);
