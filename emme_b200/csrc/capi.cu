@@ -22,6 +22,8 @@
 #include "qr.h"
 #include "run_const.h"
 
+static_assert(EMME_MAX_PEERS == EMME_MAX_PEER_RANKS, "peer group size: csrc/assembly.h and include/emme_b200.h disagree");
+
 using emme::RunConst;
 typedef std::complex<double> zc;
 
