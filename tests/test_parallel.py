@@ -189,3 +189,34 @@ def test_column_block_ownership_covers_every_block():
                     assert all(b % P == me and b > K for b in blocks)
                     seen += blocks
                 assert sorted(seen) == list(range(K + 1, nb))
+
+
+def test_item_order_visits_every_pair_once():
+    """Kernel 1's item order restated (csrc/assembly.cu::decode_pair): pairs diagonal-major (d = j - i
+    ascending), inside a diagonal alternating between its two ends (0, L-1, 1, L-2, ...) so that a
+    cohort of 32 items holds 16 neighbours and their 16 mirror images.  Every pair i < j exactly once."""
+    def decode(p, N):
+        # closed form for the diagonal with an integer fix-up, as on the device
+        tn = 2.0 * N + 1.0
+        disc = max(tn * tn - 8.0 * (N + p), 0.0)
+        d = int(np.floor((tn - np.sqrt(disc)) * 0.5))
+        d = min(max(d, 1), N - 1)
+        while d > 1 and (d - 1) * (2 * N - d) // 2 > p:
+            d -= 1
+        while d < N - 1 and d * (2 * N - d - 1) // 2 <= p:
+            d += 1
+        base = (d - 1) * (2 * N - d) // 2
+        L, t = N - d, p - base
+        i = (L - 1 - (t >> 1)) if (t & 1) else (t >> 1)
+        return i, i + d
+    for N in (2, 3, 7, 32, 33, 100):
+        pairs = [decode(p, N) for p in range(N * (N - 1) // 2)]
+        assert len(set(pairs)) == len(pairs) == N * (N - 1) // 2
+        assert all(0 <= i < j < N for i, j in pairs)
+        ds = [j - i for i, j in pairs]
+        assert ds == sorted(ds)                                   # diagonal-major
+    # mirror pairing: consecutive even/odd positions of a diagonal are mirror images of each other
+    N = 64
+    first = [decode(p, N) for p in range(8)]                      # diagonal d = 1, L = 63
+    assert first[:4] == [(0, 1), (62, 63), (1, 2), (61, 62)]
+    assert all(first[2 * k][0] + first[2 * k + 1][1] == N - 1 for k in range(4))
