@@ -1,5 +1,5 @@
 // scratch/panel_bench.cu -- phase timing of panel_sym_kernel (clock64 at phase boundaries of CTA 0).
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DEMME_PS_CLOCKS -o scratch/panel_bench scratch/panel_bench.cu
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DEMME_PS_CLOCKS -o scratch/panel_bench scratch/panel_bench.cu emme_b200/csrc/peer.cu
 #include <cstdio>
 #include <vector>
 #include "../emme_b200/csrc/dense.cu"
