@@ -8,8 +8,9 @@
 //
 // Mapping (round-1 profile r1a motivated the change from "lane = node"):
 //   * a work item is one adaptive quadrature (pair i<j, mode m); items are ordered mode-major,
-//     pairs diagonal-major (d = j-i ascending), so consecutive items are near-identical
-//     integrals (same |i-j|, neighbouring eta) and the most expensive ones run first;
+//     pairs diagonal-major (d = j-i), so consecutive items are near-identical integrals (same
+//     |i-j|, neighbouring eta); the expensive diagonals run first: the far ones (long Miller
+//     recurrences) where the geometry makes them costly, then d = 1, 2, ... (decode_pair);
 //   * a LANE owns one item and walks its panels; the 32 lanes of a warp walk the 15 (31)
 //     Kronrod nodes of their current panels in lockstep (node index j is warp-uniform), so
 //     - the Miller recurrences of neighbouring integrals at the same node have nearly the
@@ -51,19 +52,38 @@ constexpr int TRIG_PANELS = (1 << (TRIG_DEPTH + 1)) - 1;   // heap-ordered panel
 #endif
 constexpr int MIN_BLOCKS = EMME_ASM_MIN_BLOCKS;
 
-// pair index p (diagonal-major: d = j-i ascending, i ascending) -> (i, j).
-// pairs with diagonal < d: T(d) = (d-1)*(2N-d)/2
-__device__ __forceinline__ void decode_pair(unsigned long long p, int N, int& i, int& j) {
-    const double tn = 2.0 * N + 1.0;
-    double disc = tn * tn - 8.0 * ((double)N + (double)p);
-    if (disc < 0.) disc = 0.;
-    long long d = (long long)floor((tn - sqrt(disc)) * 0.5);
-    if (d < 1) d = 1;
-    if (d > N - 1) d = N - 1;
-    // fix up rounding of the closed form
-    while (d > 1 && (unsigned long long)((d - 1) * (2LL * N - d) / 2) > p) --d;
-    while (d < N - 1 && (unsigned long long)(d * (2LL * N - d - 1) / 2) <= p) ++d;
-    const unsigned long long base = (unsigned long long)((d - 1) * (2LL * N - d) / 2);
+// pair index p -> (i, j).  Diagonal-major (d = j-i); pairs with diagonal < d: T(d) = (d-1)*(2N-d)/2.
+// d_split = 0: d = 1, 2, ..., N-1.  d_split > 0: the far diagonals first, d = N-1 down to d_split
+// (lengths 1, 2, ...), then d = 1 .. d_split-1.  Where the Bessel argument grows with |eta| (every
+// geometry: b ~ k_rho^2 (1 + s^2 eta^2)) the far pairs carry the longest Miller recurrences and are
+// the costliest items after the near-singular ones; left at the end of the queue they are the tail of
+// the launch (C1: the last cohorts cost 1.5x the mean, 5.5 cohorts per warp).  The host decides
+// (capi.cu::choose_item_order); the entries do not depend on the order.
+__device__ __forceinline__ void decode_pair(unsigned long long p, int N, int d_split, int& i, int& j) {
+    long long d;
+    unsigned long long base;
+    // far diagonals first: d = N-1, N-2, ..., d_split (lengths 1, 2, ...), then d = 1 .. d_split-1
+    const unsigned long long n_far = d_split > 0 ? (unsigned long long)(N - d_split) * (N - d_split + 1) / 2 : 0ULL;
+    if (p < n_far) {
+        long long L = (long long)floor((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+        if (L < 1) L = 1;
+        while (L > 1 && (unsigned long long)(L * (L - 1) / 2) > p) --L;
+        while ((unsigned long long)(L * (L + 1) / 2) <= p) ++L;
+        d = N - L;
+        base = (unsigned long long)(L * (L - 1) / 2);
+    } else {
+        p -= n_far;
+        const double tn = 2.0 * N + 1.0;
+        double disc = tn * tn - 8.0 * ((double)N + (double)p);
+        if (disc < 0.) disc = 0.;
+        d = (long long)floor((tn - sqrt(disc)) * 0.5);
+        if (d < 1) d = 1;
+        if (d > N - 1) d = N - 1;
+        // fix up rounding of the closed form
+        while (d > 1 && (unsigned long long)((d - 1) * (2LL * N - d) / 2) > p) --d;
+        while (d < N - 1 && (unsigned long long)(d * (2LL * N - d - 1) / 2) <= p) ++d;
+        base = (unsigned long long)((d - 1) * (2LL * N - d) / 2);
+    }
     // Position t on the diagonal -> row i, alternating between the two ends (0, L-1, 1, L-2, ...):
     // a cohort of 32 consecutive items then holds 16 neighbouring pairs and their 16 mirror images
     // (eta -> -eta), which cost the same on the symmetric geometries, instead of 32 neighbours -- the
@@ -136,7 +156,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                 unsigned long long n_items_local, unsigned long long shard_index,
                 unsigned long long shard_count, unsigned long long* __restrict__ counter,
                 double2* __restrict__ spill, int spill_cap, unsigned long long* __restrict__ stats,
-                int refill_min, const NodeConst* __restrict__ table) {
+                int refill_min, const NodeConst* __restrict__ table, int d_split) {
     constexpr int H = (ORDER - 1) / 2;          // 7 or 15 symmetric node pairs
     const GKTables& T = ORDER == 15 ? c_gk15 : c_gk31;
 
@@ -177,7 +197,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                     // shards take chunks of 32 consecutive items round-robin
                     const unsigned long long kg = (k >> 5) * (shard_count << 5) + (shard_index << 5) + (k & 31);
                     it_m = (int)(kg / n_pairs);
-                    decode_pair(kg - (unsigned long long)it_m * n_pairs, rc.N, it_i, it_j);
+                    decode_pair(kg - (unsigned long long)it_m * n_pairs, rc.N, d_split, it_i, it_j);
                     {
                         const PairConst c = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
                         volatile double* ps = &s_pair[0][threadIdx.x];
@@ -402,7 +422,7 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
                             const double* bi, const PeerSet& A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,
                             unsigned long long* stats, int grid_blocks, cudaStream_t stream,
-                            unsigned long long* n_launches, int refill_min, void* table) {
+                            unsigned long long* n_launches, int refill_min, void* table, int d_split) {
     const unsigned long long N = rc.N;
     const unsigned long long n_items = N * (N - 1) / 2 * (rc.em ? 3ULL : 1ULL);
     const unsigned long long sc = shard_count, si = shard_index;
@@ -415,6 +435,7 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
         const unsigned long long last_chunk = (my_chunks - 1) * sc + si;   // global index
         if (last_chunk == n_chunks - 1) n_local -= n_chunks * 32 - n_items;
     }
+    if (d_split < 2 || d_split > rc.N - 1) d_split = 0;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
@@ -431,11 +452,11 @@ cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double*
         if (rc.order == 15) {
             assemble_kernel<15><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats, refill_min, (const NodeConst*)table);
+                stats, refill_min, (const NodeConst*)table, d_split);
         } else {
             assemble_kernel<31><<<grid_blocks, BLOCK, 0, stream>>>(
                 rc, eta, g, bi, A, n_local, si, sc, counter, (double2*)spill, spill_cap,
-                stats, refill_min, (const NodeConst*)table);
+                stats, refill_min, (const NodeConst*)table, d_split);
         }
     }
     return cudaGetLastError();

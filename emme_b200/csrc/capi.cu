@@ -91,6 +91,7 @@ struct emme_solver {
     emme_stats stats{};
     unsigned long long launches = 0;
     int refill_min = 32;
+    int d_split = 0;                  // kernel 1's item order: diagonals >= d_split first (0: d = 1, 2, ...)
     int optimistic = 1;               // try the interchange-free factorisation first
     int null_optimistic = 1;
     int use_graph = 1;                // replay the optimistic dense step as a CUDA graph
@@ -131,6 +132,21 @@ int emme_fp64_peak(int device, double* tflops, double* sm_mhz_nominal) {
     return 0;
 }
 
+// Item order of kernel 1 (assembly.cu::decode_pair).  The Miller recurrence of a pair starts at
+// floor(|z|) + 1 with |z| = sqrt(b b') / |lambda|.  Where sqrt(b b') of the pairs that span the mesh is
+// large, the recurrence outweighs the rest of an evaluation and the far diagonals are the costliest
+// items after the near-singular ones, so they go first.  Measured (profiles/r2_order_sweep.txt): C1
+// physics, sqrt(b_0 b_N-1) = 24.7: N = 512 0.77 -> 0.68 ms, N = 1024 1.94 -> 1.84, N = 2048 6.71 -> 6.59,
+// neutral from 4096 up; C3 (6.5: |z| <= 9, far pairs are the cheapest items) 0.881 -> 0.894 ms, so it
+// keeps the plain order.  The switch sits between the two.
+// EMME_ASM_FAR_SPLIT=f overrides: diagonals d >= f*N first, 0 = plain order.
+static void choose_item_order(emme_solver* s, const double* bi) {
+    double frac = std::sqrt(std::fabs(bi[0] * bi[s->N - 1])) >= 16.0 ? 0.5 : 0.0;
+    if (const char* e = std::getenv("EMME_ASM_FAR_SPLIT")) frac = std::atof(e);
+    s->d_split = (frac > 0.0 && frac < 1.0) ? (int)(frac * s->N) : 0;
+    if (s->d_split < 2) s->d_split = 0;
+}
+
 int emme_set_tables(emme_solver* s, const double* eta, const double* g, const double* bi) {
     if (!s) return fail(-1, "null handle");
     if (!eta) return fail(-2, "null eta");
@@ -141,6 +157,7 @@ int emme_set_tables(emme_solver* s, const double* eta, const double* g, const do
     CU(cudaMemcpyAsync(s->d_eta, eta, tb, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->d_g, g, tb, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->d_bi, bi, tb, cudaMemcpyHostToDevice, s->stream));
+    choose_item_order(s, bi);
     return 0;
 }
 
@@ -244,6 +261,7 @@ int emme_create(const emme_params* p, int npoints, const double* eta, const doub
     CU(cudaMemcpy(s->d_eta, eta, tb, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_g, g, tb, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_bi, bi, tb, cudaMemcpyHostToDevice));
+    choose_item_order(s.get(), bi);
     CU(cudaMalloc(&s->A, s->bytes()));
     CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_stats, 8 * sizeof(unsigned long long)));
@@ -350,7 +368,7 @@ static int enqueue_assembly(emme_solver* s, zc w, void* dst, int shard_index, in
     CU(cudaEventRecord(s->ev0, s->stream));
     CU(emme::launch_assembly(rc, s->d_eta, s->d_g, s->d_bi, ps, shard_index, shard_count,
                              s->d_counter, s->d_spill, s->spill_cap, s->d_stats, s->launch_blocks,
-                             s->stream, &s->launches, s->refill_min, s->d_trig));
+                             s->stream, &s->launches, s->refill_min, s->d_trig, s->d_split));
     CU(cudaEventRecord(s->ev1, s->stream));
     return 0;
 }

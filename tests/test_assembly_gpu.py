@@ -112,6 +112,27 @@ def test_sharded_assembly_sums_to_full(native_lib):
     assert np.array_equal(acc, full)
 
 
+@pytest.mark.parametrize("case", ["c1_n64", "c1_em_n64", "c3_n64"])
+def test_entries_do_not_depend_on_the_item_order(case, native_lib, monkeypatch):
+    """Kernel 1's item order (far diagonals first where the host finds them costly,
+    capi.cu::choose_item_order) only schedules: every order gives the same matrix bit for bit."""
+    inp = Input(cases.input_path(case))
+    _, n = inp.params()
+    w = inp.initial_guess()
+    mats = []
+    for split in (None, "0", "0.5", "0.9", "0.04"):
+        if split is None:
+            monkeypatch.delenv("EMME_ASM_FAR_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("EMME_ASM_FAR_SPLIT", split)
+        s = EigenSolver.from_input(inp)
+        mats.append(s.matrixAssembler(w))
+        assert s.stats()["integrals"] == n * (n - 1) // 2 * (3 if s.dim == 2 * n else 1)
+        s.close()
+    for m in mats[1:]:
+        assert np.array_equal(m, mats[0])
+
+
 def test_deep_stack_spills_to_global(native_lib):
     """Tight tolerances force deep bisection: the interval stack must follow the reference's
     contract (depth <= integration_iteration_limit), past the shared-memory slots."""

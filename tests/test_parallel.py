@@ -192,20 +192,31 @@ def test_column_block_ownership_covers_every_block():
 
 
 def test_item_order_visits_every_pair_once():
-    """Kernel 1's item order restated (csrc/assembly.cu::decode_pair): pairs diagonal-major (d = j - i
-    ascending), inside a diagonal alternating between its two ends (0, L-1, 1, L-2, ...) so that a
-    cohort of 32 items holds 16 neighbours and their 16 mirror images.  Every pair i < j exactly once."""
-    def decode(p, N):
-        # closed form for the diagonal with an integer fix-up, as on the device
-        tn = 2.0 * N + 1.0
-        disc = max(tn * tn - 8.0 * (N + p), 0.0)
-        d = int(np.floor((tn - np.sqrt(disc)) * 0.5))
-        d = min(max(d, 1), N - 1)
-        while d > 1 and (d - 1) * (2 * N - d) // 2 > p:
-            d -= 1
-        while d < N - 1 and d * (2 * N - d - 1) // 2 <= p:
-            d += 1
-        base = (d - 1) * (2 * N - d) // 2
+    """Kernel 1's item order restated (csrc/assembly.cu::decode_pair): pairs diagonal-major (d = j - i),
+    inside a diagonal alternating between its two ends (0, L-1, 1, L-2, ...) so that a cohort of 32
+    items holds 16 neighbours and their 16 mirror images.  d_split = 0: d ascending; d_split > 0: the far
+    diagonals first (d = N-1 down to d_split), then d = 1 .. d_split-1.  Every pair i < j exactly once."""
+    def decode(p, N, d_split=0):
+        # closed forms for the diagonal with integer fix-ups, as on the device
+        n_far = (N - d_split) * (N - d_split + 1) // 2 if d_split > 0 else 0
+        if p < n_far:
+            L = max(int(np.floor((1.0 + np.sqrt(1.0 + 8.0 * p)) * 0.5)), 1)
+            while L > 1 and L * (L - 1) // 2 > p:
+                L -= 1
+            while L * (L + 1) // 2 <= p:
+                L += 1
+            d, base = N - L, L * (L - 1) // 2
+        else:
+            p -= n_far
+            tn = 2.0 * N + 1.0
+            disc = max(tn * tn - 8.0 * (N + p), 0.0)
+            d = int(np.floor((tn - np.sqrt(disc)) * 0.5))
+            d = min(max(d, 1), N - 1)
+            while d > 1 and (d - 1) * (2 * N - d) // 2 > p:
+                d -= 1
+            while d < N - 1 and d * (2 * N - d - 1) // 2 <= p:
+                d += 1
+            base = (d - 1) * (2 * N - d) // 2
         L, t = N - d, p - base
         i = (L - 1 - (t >> 1)) if (t & 1) else (t >> 1)
         return i, i + d
@@ -215,8 +226,18 @@ def test_item_order_visits_every_pair_once():
         assert all(0 <= i < j < N for i, j in pairs)
         ds = [j - i for i, j in pairs]
         assert ds == sorted(ds)                                   # diagonal-major
+    for N, d_split in ((7, 3), (32, 16), (33, 16), (33, 2), (33, 32), (100, 50), (1024, 512)):
+        n = N * (N - 1) // 2
+        pairs = [decode(p, N, d_split) for p in range(n)]
+        assert len(set(pairs)) == n and all(0 <= i < j < N for i, j in pairs)
+        ds = [j - i for i, j in pairs]
+        n_far = (N - d_split) * (N - d_split + 1) // 2
+        assert ds[:n_far] == sorted(ds[:n_far], reverse=True) and min(ds[:n_far]) == d_split
+        assert ds[n_far:] == sorted(ds[n_far:]) and (n_far == n or max(ds[n_far:]) == d_split - 1)
     # mirror pairing: consecutive even/odd positions of a diagonal are mirror images of each other
     N = 64
     first = [decode(p, N) for p in range(8)]                      # diagonal d = 1, L = 63
     assert first[:4] == [(0, 1), (62, 63), (1, 2), (61, 62)]
     assert all(first[2 * k][0] + first[2 * k + 1][1] == N - 1 for k in range(4))
+    far = [decode(p, N, 32) for p in range(6)]                    # d = 63 (1 pair), 62 (2), 61 (3)
+    assert far == [(0, 63), (0, 62), (1, 63), (0, 61), (2, 63), (1, 62)]
