@@ -7,10 +7,11 @@
 // SingularityHandler (src/singularity_handler.cpp:3-24) and the DedicatedThreadPool fan-out.
 //
 // Mapping (round-1 profile r1a motivated the change from "lane = node"):
-//   * a work item is one adaptive quadrature (pair i<j, mode m); items are ordered mode-major,
-//     pairs diagonal-major (d = j-i), so consecutive items are near-identical integrals (same
-//     |i-j|, neighbouring eta); the expensive diagonals run first: the far ones (long Miller
-//     recurrences) where the geometry makes them costly, then d = 1, 2, ... (decode_pair);
+//   * a work item is one adaptive quadrature (pair i<j, mode m); items are ordered diagonal-major
+//     (d = j-i), the modes of an EM run inside each diagonal, so consecutive items are
+//     near-identical integrals (same |i-j|, same m, neighbouring eta); the expensive diagonals run
+//     first: the far ones (long Miller recurrences) where the geometry makes them costly, then
+//     d = 1, 2, ... (decode_item);
 //   * a LANE owns one item and walks its panels; the 32 lanes of a warp walk the 15 (31)
 //     Kronrod nodes of their current panels in lockstep (node index j is warp-uniform), so
 //     - the Miller recurrences of neighbouring integrals at the same node have nearly the
@@ -52,17 +53,23 @@ constexpr int TRIG_PANELS = (1 << (TRIG_DEPTH + 1)) - 1;   // heap-ordered panel
 #endif
 constexpr int MIN_BLOCKS = EMME_ASM_MIN_BLOCKS;
 
-// pair index p -> (i, j).  Diagonal-major (d = j-i); pairs with diagonal < d: T(d) = (d-1)*(2N-d)/2.
+// item index k -> (i, j, m).  Diagonal-major (d = j-i); pairs on diagonals before d in the plain
+// order: T(d) = (d-1)*(2N-d)/2.  The nm modes of an electromagnetic run (3 integrals per pair) sit
+// INSIDE the diagonal -- all pairs of diagonal d for m = 0, then m = 1, then m = 2 -- so that cohorts
+// stay uniform in m and the near-singular diagonals of every mode run first.  (Mode-major, the order
+// of rounds 1-2, started the deep bisections of m = 1, 2 one and two thirds into the queue: in C3 one
+// such cohort lasts longer than the balanced share of a warp, so they set the length of the launch.)
 // d_split = 0: d = 1, 2, ..., N-1.  d_split > 0: the far diagonals first, d = N-1 down to d_split
 // (lengths 1, 2, ...), then d = 1 .. d_split-1.  Where the Bessel argument grows with |eta| (every
 // geometry: b ~ k_rho^2 (1 + s^2 eta^2)) the far pairs carry the longest Miller recurrences and are
 // the costliest items after the near-singular ones; left at the end of the queue they are the tail of
 // the launch (C1: the last cohorts cost 1.5x the mean, 5.5 cohorts per warp).  The host decides
 // (capi.cu::choose_item_order); the entries do not depend on the order.
-__device__ __forceinline__ void decode_pair(unsigned long long p, int N, int d_split, int& i, int& j) {
+__device__ __forceinline__ void decode_item(unsigned long long k, int N, int nm, int d_split, int& i, int& j,
+                                            int& m) {
+    unsigned long long p = k / (unsigned)nm;     // a pair on the item's diagonal
     long long d;
-    unsigned long long base;
-    // far diagonals first: d = N-1, N-2, ..., d_split (lengths 1, 2, ...), then d = 1 .. d_split-1
+    unsigned long long base;                      // pairs on the diagonals that come before d in this order
     const unsigned long long n_far = d_split > 0 ? (unsigned long long)(N - d_split) * (N - d_split + 1) / 2 : 0ULL;
     if (p < n_far) {
         long long L = (long long)floor((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
@@ -82,15 +89,17 @@ __device__ __forceinline__ void decode_pair(unsigned long long p, int N, int d_s
         // fix up rounding of the closed form
         while (d > 1 && (unsigned long long)((d - 1) * (2LL * N - d) / 2) > p) --d;
         while (d < N - 1 && (unsigned long long)(d * (2LL * N - d - 1) / 2) <= p) ++d;
-        base = (unsigned long long)((d - 1) * (2LL * N - d) / 2);
+        base = n_far + (unsigned long long)((d - 1) * (2LL * N - d) / 2);
     }
+    const int L = N - (int)d;
+    const unsigned r = (unsigned)(k - (unsigned long long)nm * base);    // position among the nm*L items of d
+    m = (int)(r / (unsigned)L);
+    const int t = (int)(r - (unsigned)m * (unsigned)L);
     // Position t on the diagonal -> row i, alternating between the two ends (0, L-1, 1, L-2, ...):
     // a cohort of 32 consecutive items then holds 16 neighbouring pairs and their 16 mirror images
     // (eta -> -eta), which cost the same on the symmetric geometries, instead of 32 neighbours -- the
     // spread of Miller trip counts inside a warp halves (it matters on small grids, where 32
     // neighbours span a wide range of eta: N = 1024 ran at 28.2 of 32 lanes per instruction).
-    const int L = N - (int)d;
-    const int t = (int)(p - base);
     i = (t & 1) ? (L - 1 - (t >> 1)) : (t >> 1);
     j = i + (int)d;
 }
@@ -172,7 +181,6 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
     double2* my_spill =
         spill ? spill + ((size_t)blockIdx.x * BLOCK + threadIdx.x) * (size_t)spill_cap : nullptr;
 
-    const unsigned long long n_pairs = (unsigned long long)rc.N * (rc.N - 1) / 2;
     bool active = false;
     bool warp_exhausted = false;
     int it_i = 0, it_j = 0, it_m = 0, top = 0, pid = 0;
@@ -196,8 +204,7 @@ assemble_kernel(const RunConst rc, const double* __restrict__ eta, const double*
                 } else {
                     // shards take chunks of 32 consecutive items round-robin
                     const unsigned long long kg = (k >> 5) * (shard_count << 5) + (shard_index << 5) + (k & 31);
-                    it_m = (int)(kg / n_pairs);
-                    decode_pair(kg - (unsigned long long)it_m * n_pairs, rc.N, d_split, it_i, it_j);
+                    decode_item(kg, rc.N, rc.em ? 3 : 1, d_split, it_i, it_j, it_m);
                     {
                         const PairConst c = make_pair(rc, eta[it_i], eta[it_j], gt[it_i], gt[it_j], bt[it_i], bt[it_j]);
                         volatile double* ps = &s_pair[0][threadIdx.x];

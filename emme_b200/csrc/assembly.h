@@ -22,7 +22,7 @@ int assembly_stack_smem();
 // and `spill` (grid_blocks*groups_per_block*spill_cap double2, may be null when
 // spill_cap == 0) are device scratch owned by the handle.  refill_min: idle lanes of a warp
 // refill together once at least this many are idle (1 = per lane, 32 = whole-warp batches).
-// d_split: item order, diagonals d >= d_split first (0: d = 1, 2, ...; see decode_pair).
+// d_split: item order, diagonals d >= d_split first (0: d = 1, 2, ...; see decode_item).
 cudaError_t launch_assembly(const RunConst& rc, const double* eta, const double* g,
                             const double* bi, const PeerSet& A, int shard_index, int shard_count,
                             unsigned long long* counter, void* spill, int spill_cap,

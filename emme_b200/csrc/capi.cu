@@ -132,7 +132,7 @@ int emme_fp64_peak(int device, double* tflops, double* sm_mhz_nominal) {
     return 0;
 }
 
-// Item order of kernel 1 (assembly.cu::decode_pair).  The Miller recurrence of a pair starts at
+// Item order of kernel 1 (assembly.cu::decode_item).  The Miller recurrence of a pair starts at
 // floor(|z|) + 1 with |z| = sqrt(b b') / |lambda|.  Where sqrt(b b') of the pairs that span the mesh is
 // large, the recurrence outweighs the rest of an evaluation and the far diagonals are the costliest
 // items after the near-singular ones, so they go first.  Measured (profiles/r2_order_sweep.txt): C1

@@ -192,7 +192,7 @@ def test_column_block_ownership_covers_every_block():
 
 
 def test_item_order_visits_every_pair_once():
-    """Kernel 1's item order restated (csrc/assembly.cu::decode_pair): pairs diagonal-major (d = j - i),
+    """Kernel 1's item order restated (csrc/assembly.cu::decode_item): pairs diagonal-major (d = j - i),
     inside a diagonal alternating between its two ends (0, L-1, 1, L-2, ...) so that a cohort of 32
     items holds 16 neighbours and their 16 mirror images.  d_split = 0: d ascending; d_split > 0: the far
     diagonals first (d = N-1 down to d_split), then d = 1 .. d_split-1.  Every pair i < j exactly once."""
@@ -241,3 +241,25 @@ def test_item_order_visits_every_pair_once():
     assert all(first[2 * k][0] + first[2 * k + 1][1] == N - 1 for k in range(4))
     far = [decode(p, N, 32) for p in range(6)]                    # d = 63 (1 pair), 62 (2), 61 (3)
     assert far == [(0, 63), (0, 62), (1, 63), (0, 61), (2, 63), (1, 62)]
+
+    # electromagnetic runs: the three integrals of a pair are three items; the modes sit inside the
+    # diagonal (all pairs of d for m = 0, then m = 1, then m = 2)
+    def decode_item(k, N, nm, d_split=0):
+        i, j = decode(k // nm, N, d_split)            # some pair on the item's diagonal
+        d, L = j - i, N - (j - i)
+        n_far = (N - d_split) * (N - d_split + 1) // 2 if d_split > 0 else 0
+        base = (N - d) * (N - d - 1) // 2 if (d_split > 0 and d >= d_split) else n_far + (d - 1) * (2 * N - d) // 2
+        r = k - nm * base
+        m, t = divmod(r, L)
+        i = (L - 1 - (t >> 1)) if (t & 1) else (t >> 1)
+        return i, i + d, m
+    for N, d_split in ((2, 0), (7, 0), (33, 0), (33, 16), (64, 32), (100, 50)):
+        n = 3 * N * (N - 1) // 2
+        items = [decode_item(k, N, 3, d_split) for k in range(n)]
+        assert len(set(items)) == n and all(0 <= i < j < N and 0 <= m < 3 for i, j, m in items)
+        # a diagonal's items are contiguous, mode by mode
+        key = [(j - i, m) for i, j, m in items]
+        assert all(key[k] == key[k + 1] or key[k] not in key[k + 1:] for k in range(0, n - 1, max(1, n // 97)))
+    assert [decode_item(k, 5, 3) for k in range(12)] == [(0, 1, 0), (3, 4, 0), (1, 2, 0), (2, 3, 0),
+                                                          (0, 1, 1), (3, 4, 1), (1, 2, 1), (2, 3, 1),
+                                                          (0, 1, 2), (3, 4, 2), (1, 2, 2), (2, 3, 2)]
